@@ -1,0 +1,134 @@
+/* g16b200.h -- C ABI of libg16b200.so, a B200-native Groth16 (BN254) prover.
+ *
+ * Drop-in boundary for the ONE step the reference shells out for:
+ *     execSync(`sunspot prove ${acir} ${witness.gz} ${ccs} ${pk}`)
+ *         /root/reference/client/proof.helper.ts:58-66
+ *     same argv in noir_circuit/prove_linux.sh:83, audit_circuit/prove_audit.sh:95,
+ *     scripts/generate_audit.py:680, scripts/benchmark_all.py:683
+ * and for the files that step leaves behind (`<name>.proof`, `<name>.pw`,
+ * client/proof.helper.ts:68-69, client/generate-proof-hex.ts:18-27).
+ *
+ * Conventions
+ *   - every function returns 0 (G16_OK) or a G16_E_* code; g16_last_error() gives the
+ *     thread-local message for the last failure on the calling thread.
+ *   - the caller owns every host buffer; the library owns device memory behind the opaque
+ *     handles.  A proving key is uploaded (and expanded into window tables) ONCE per
+ *     g16_circuit and reused for every proof.
+ *   - wire formats are gnark's: Fr = 32 B big-endian canonical; G1 = X||Y (64 B raw);
+ *     G2 = X.A1||X.A0||Y.A1||Y.A0 (128 B raw); infinity = 0x40 then zeros.
+ *   - "dev" entry points take DEVICE pointers (e.g. torch tensors' data_ptr()) holding
+ *     little-endian 8x32-bit limbs; they only enqueue work on the context stream.
+ *   - there is no CPU fallback: every compute entry point fails with G16_E_CUDA when no
+ *     sm_100-class device is usable.
+ */
+#ifndef G16B200_H
+#define G16B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    G16_OK = 0,
+    G16_E_ARG = 1,
+    G16_E_PARSE = 2,  /* malformed .ccs / .pk / witness */
+    G16_E_UNSAT = 3,  /* witness does not satisfy the R1CS (message names the row) */
+    G16_E_CUDA = 4,
+    G16_E_HINT = 5,   /* unknown / failing solver hint */
+    G16_E_NOMEM = 6,
+    G16_E_INTERNAL = 7
+};
+
+#define G16_PROOF_LEN 388 /* shielded_pool_program/src/instructions/withdraw.rs:13, submit_audit.rs:18 */
+
+typedef struct g16_ctx g16_ctx;
+typedef struct g16_circuit g16_circuit;
+typedef struct g16_bases g16_bases;
+
+/* ---- context ------------------------------------------------------------------------- */
+/* One context drives one GPU (one process per GPU under torchrun).  n_devices must be 1. */
+int g16_init(const int* device_ids, int n_devices, g16_ctx** out);
+void g16_shutdown(g16_ctx* ctx);
+const char* g16_last_error(void);
+/* Run all subsequent work of `ctx` on the caller's CUDA stream (a cudaStream_t, e.g.
+ * torch.cuda.current_stream().cuda_stream); NULL restores the context's own stream. */
+int g16_set_stream(g16_ctx* ctx, void* cuda_stream);
+int g16_sync(g16_ctx* ctx);
+/* kernels launched by the last compute call on this context (bench.py `gpu_launches`) */
+int g16_last_launches(g16_ctx* ctx);
+/* Integer-pipe microbenchmark: kind 0 = IMAD (mad.lo.u32), 1 = IMAD.WIDE.U32 with carry
+ * (mad.lo.cc/madc.hi.cc pairs, the instruction the field multiplier is made of).
+ * Writes instructions per second over the whole chip. */
+int g16_measure_imad_peak(g16_ctx* ctx, int kind, double* instr_per_s);
+
+/* ---- standalone kernels ("kernels exposed for the sweep") ------------------ */
+/* Upload n bases and expand them into window tables.  window = 0 picks one for
+ * (n, batch_hint).  Replaces the pk.G1.{A,B,K,Z} / pk.G2.B slices gnark keeps on the heap. */
+int g16_bases_load_g1(g16_ctx* ctx, const uint8_t* points_be, size_t n, int window, size_t batch_hint,
+                      g16_bases** out);
+int g16_bases_load_g2(g16_ctx* ctx, const uint8_t* points_be, size_t n, int window, size_t batch_hint,
+                      g16_bases** out);
+void g16_bases_free(g16_bases* b);
+int g16_bases_window(const g16_bases* b);
+/* out[b] = sum_i scalars[b][i] * P_i  -- replaces G1Jac.MultiExp / G2Jac.MultiExp.
+ * scalars_be: batch*n*32 B; out_be: batch*64 B (G1) / batch*128 B (G2). Host buffers. */
+int g16_msm_g1(g16_ctx* ctx, const g16_bases* bases, const uint8_t* scalars_be, size_t batch, uint8_t* out_be);
+int g16_msm_g2(g16_ctx* ctx, const g16_bases* bases, const uint8_t* scalars_be, size_t batch, uint8_t* out_be);
+/* Device-resident variant: d_scalars = batch*n Fr (8 LE limbs, Montgomery iff montgomery!=0),
+ * d_out = batch affine points in Montgomery limb form.  Asynchronous on the context stream. */
+int g16_msm_dev(g16_ctx* ctx, const g16_bases* bases, const void* d_scalars, int montgomery, size_t batch,
+                void* d_out);
+
+/* Synthetic bases for the kernel sweep / throughput runs:
+ * P_i = [k_i]G, k_i = 253-bit value built from SplitMix64(seed + 4i .. 4i+3), computed on the
+ * device; written as gnark raw points to a host buffer (n*64 B, or n*128 B when g2 != 0). */
+int g16_generate_points(g16_ctx* ctx, int g2, uint64_t seed, size_t n, uint8_t* out_be);
+
+/* In-place Fr NTT of `batch` vectors of length n = 2^logn (replaces gnark-crypto fr/fft
+ * Domain.FFT / FFTInverse).
+ *   inverse = 0: natural-order input  -> bit-reversed output (DIF), optional coset shift g=5 first
+ *   inverse = 1: bit-reversed input   -> natural-order output (DIT), 1/n and optional g^-j after
+ * values_be: batch*n*32 B big-endian canonical, transformed in place (host buffer). */
+int g16_ntt(g16_ctx* ctx, uint8_t* values_be, unsigned logn, size_t batch, int inverse, int coset);
+/* device-resident variant: d_values = batch*n Fr in Montgomery limb form */
+int g16_ntt_dev(g16_ctx* ctx, void* d_values, unsigned logn, size_t batch, int inverse, int coset);
+
+/* ---- circuits and proofs ---------------------------------------------------------------- */
+/* Parse a gnark v0.14 R1CS (.ccs) and proving key (.pk), upload and expand the key.
+ * acir_json may be NULL: the .ccs `Public`/`Secret` name lists carry the witness mapping. */
+int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uint8_t* pk, size_t pk_len,
+                     const char* acir_json, g16_circuit** out);
+void g16_circuit_free(g16_circuit* c);
+/* sizes: what[0]=nbConstraints [1]=nbWires [2]=nbPublic(incl. ONE) [3]=nbSecret [4]=domain size
+ *        [5]=nbCommitments [6..10] = MSM sizes A,B,K,Z,commit */
+int g16_circuit_info(const g16_circuit* c, uint64_t what[16]);
+
+/* One proof from a Noir witness (`target/<name>.gz`, as written by `nargo execute`).
+ * rnd = r || s || commitment blinder (3 x 32 B big-endian); NULL draws them from the OS CSPRNG.
+ * proof: G16_PROOF_LEN bytes (gnark Proof.WriteRawTo); pw: 12 + 32*nPublic bytes (witness.WriteTo,
+ * public part).  *_len: in = capacity, out = bytes written. */
+int g16_prove(g16_circuit* c, const uint8_t* witness_gz, size_t witness_len, const uint8_t rnd[96],
+              uint8_t* proof, size_t* proof_len, uint8_t* pw, size_t* pw_len);
+/* Same, from the public+secret assignment directly (32 B big-endian each, `.ccs` order:
+ * Public[1..] then Secret[..]) -- skips the Noir container, runs the R1CS solver. */
+int g16_prove_assignment(g16_circuit* c, const uint8_t* assignment_be, size_t n_values, const uint8_t rnd[96],
+                         uint8_t* proof, size_t* proof_len, uint8_t* pw, size_t* pw_len);
+/* n independent proofs of the same circuit in one device batch.  assignments_be = n *
+ * n_values * 32 B; rnd = n*96 B or NULL; proofs = n*388 B; pws = n*pw_stride B. */
+int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, size_t n_values, const uint8_t* rnd,
+                    uint8_t* proofs, uint8_t* pws, size_t pw_stride);
+/* Bypass the solver: full wire vectors (nbWires * 32 B big-endian each, wire 0 = 1).  The
+ * commitment wire must already hold the BSB22 challenge consistent with `rnd`'s blinder when a
+ * valid proof is wanted; for throughput runs any vector does identical work. */
+int g16_prove_wires(g16_circuit* c, size_t n, const uint8_t* wires_be, const uint8_t* rnd, uint8_t* proofs);
+/* Device-resident throughput path: d_wires = n * nbWires Fr in Montgomery limb form already in
+ * HBM; d_proof_points receives per proof 5 affine results (Ar, Bs1, Krs-partial, PoK in G1 and
+ * Bs in G2) in Montgomery limb form.  Asynchronous. */
+int g16_prove_wires_dev(g16_circuit* c, size_t n, const void* d_wires, void* d_proof_points);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G16B200_H */

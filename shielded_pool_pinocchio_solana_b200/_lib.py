@@ -1,0 +1,71 @@
+"""ctypes binding of libg16b200.so (include/g16b200.h).
+
+The library is the product; this module only loads it and declares prototypes.  There is no
+Python or CPU fallback: if the shared object is missing the import of any compute entry point
+raises, loudly.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libg16b200.so")
+
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+c_void_pp = ctypes.POINTER(ctypes.c_void_p)
+
+# name -> (restype, argtypes); mirrors include/g16b200.h one to one
+PROTOTYPES = {
+    "g16_init": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int, c_void_pp]),
+    "g16_shutdown": (None, [ctypes.c_void_p]),
+    "g16_last_error": (ctypes.c_char_p, []),
+    "g16_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "g16_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "g16_last_launches": (ctypes.c_int, [ctypes.c_void_p]),
+    "g16_measure_imad_peak": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+    "g16_bases_load_g1": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
+                                         ctypes.c_size_t, c_void_pp]),
+    "g16_bases_load_g2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
+                                         ctypes.c_size_t, c_void_pp]),
+    "g16_bases_free": (None, [ctypes.c_void_p]),
+    "g16_bases_window": (ctypes.c_int, [ctypes.c_void_p]),
+    "g16_msm_g1": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t,
+                                  ctypes.c_char_p]),
+    "g16_msm_g2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t,
+                                  ctypes.c_char_p]),
+    "g16_generate_points": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_size_t,
+                                           ctypes.c_char_p]),
+    "g16_msm_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                   ctypes.c_size_t, ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+class G16Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"g16b200 error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    """Load libg16b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). This package has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library drift
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().g16_last_error()
+        raise G16Error(rc, msg.decode() if msg else "")

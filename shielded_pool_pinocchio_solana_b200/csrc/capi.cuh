@@ -1,0 +1,40 @@
+// capi.cuh -- private definitions behind the opaque handles of include/g16b200.h.
+#pragma once
+#include "../../include/g16b200.h"
+#include "common.cuh"
+#include "msm.cuh"
+
+namespace g16 {
+
+struct DeviceBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    ~DeviceBuf();
+};
+
+void be32_to_limbs(const uint8_t* be, uint32_t* limbs);
+void limbs_to_be32(const uint32_t* limbs, uint8_t* be);
+void g1_from_be(const uint8_t* be, G1Affine* out);
+void g1_to_be(const G1Affine& p, uint8_t* be);
+void g2_from_be(const uint8_t* be, G2Affine* out);
+void g2_to_be(const G2Affine& p, uint8_t* be);
+
+}  // namespace g16
+
+struct g16_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int last_launches = 0;
+    g16::MsmRunner<g16::Fp> g1;
+    g16::MsmRunner<g16::Fp2> g2;
+    g16::DeviceBuf scratch, scalars, results;
+};
+
+struct g16_bases {
+    int g2 = 0;
+    g16::MsmBases<g16::Fp> b1;
+    g16::MsmBases<g16::Fp2> b2;
+};

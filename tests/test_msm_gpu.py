@@ -1,0 +1,73 @@
+"""CUDA MSM (through the C ABI) vs the big-integer oracle -- bit-exact.
+
+Reference behaviour: gnark-crypto G1Jac.MultiExp / G2Jac.MultiExp as used by `sunspot prove`
+(/root/reference/client/proof.helper.ts:64).
+"""
+import json
+import os
+import random
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "msm_small.json")
+
+
+@pytest.mark.parametrize("group", ["g1", "g2"])
+@pytest.mark.parametrize("window", [0, 4, 9, 13, 16])
+def test_msm_golden(ctx, group, window):
+    case = json.load(open(GOLDEN))[group]
+    bases = ctx.load_bases(bytes.fromhex(case["points"]), group, window=window, batch_hint=case["batch"])
+    got = bases.msm(bytes.fromhex(case["scalars"]), batch=case["batch"])
+    assert got.hex() == case["results"]
+    bases.free()
+
+
+def test_generated_points_match_oracle(ctx):
+    import bn254 as B
+    import serialize as S
+    M = (1 << 64) - 1
+
+    def splitmix64(x):
+        x = (x + 0x9e3779b97f4a7c15) & M
+        x = ((x ^ (x >> 30)) * 0xbf58476d1ce4e5b9) & M
+        x = ((x ^ (x >> 27)) * 0x94d049bb133111eb) & M
+        return x ^ (x >> 31)
+
+    def k_of(seed, i):
+        k = 0
+        for w in range(4):
+            k |= splitmix64((seed + 4 * i + w) & M) << (64 * w)
+        return k & ((1 << 253) - 1)
+
+    seed = 0xB200
+    pts = ctx.generate_points(8, seed, "g1")
+    for i in range(8):
+        assert pts[64 * i:64 * i + 64] == S.g1_to_bytes(B.g1_mul(B.G1_GEN, k_of(seed, i)))
+    pts2 = ctx.generate_points(3, seed, "g2")
+    for i in range(3):
+        assert pts2[128 * i:128 * i + 128] == S.g2_to_bytes(B.g2_mul(B.G2_GEN, k_of(seed, i)))
+
+
+@pytest.mark.parametrize("n,batch", [(1 << 12, 4), (5000, 1), (1 << 14, 2)])
+def test_msm_linearity_large(ctx, n, batch):
+    """Size-independent property at sizes the big-int oracle cannot reach quickly:
+    MSM(P, s) + MSM(P, t) == MSM(P, s + t)  and  MSM(P, e_j) == P_j."""
+    import bn254 as B
+    import serialize as S
+    rng = random.Random(n)
+    pts = ctx.generate_points(n, 0x51, "g1")
+    bases = ctx.load_bases(pts, "g1", batch_hint=3 * batch)
+    s = [[rng.randrange(B.R) for _ in range(n)] for _ in range(batch)]
+    t = [[rng.randrange(B.R) for _ in range(n)] for _ in range(batch)]
+    u = [[(a + b) % B.R for a, b in zip(sr, tr)] for sr, tr in zip(s, t)]
+    enc = lambda rows: b"".join(S.fr_to_bytes(x) for row in rows for x in row)
+    out = bases.msm(enc(s + t + u), batch=3 * batch)
+    P = [S.g1_from_bytes(out[64 * i:64 * i + 64]) for i in range(3 * batch)]
+    for b in range(batch):
+        assert B.g1_add(P[b], P[batch + b]) == P[2 * batch + b]
+    # unit vectors pick out single bases
+    j = rng.randrange(n)
+    e = [[1 if i == j else 0 for i in range(n)]]
+    assert bases.msm(enc(e), batch=1) == pts[64 * j:64 * j + 64]
+    bases.free()
