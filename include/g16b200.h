@@ -95,6 +95,15 @@ int g16_ntt(g16_ctx* ctx, uint8_t* values_be, unsigned logn, size_t batch, int i
 /* device-resident variant: d_values = batch*n Fr in Montgomery limb form */
 int g16_ntt_dev(g16_ctx* ctx, void* d_values, unsigned logn, size_t batch, int inverse, int coset);
 
+/* Quotient polynomial of Groth16 (replaces gnark computeH, backend/groth16/bn254/prove.go;
+ * SURVEY.md 8a row a6).  abc_be: per proof three vectors of n = 2^logn Fr (A.w, B.w, C.w on the
+ * domain, natural order, zero padded).  h_be: per proof n Fr = coefficients of
+ * H = (A*B - C)/(X^n - 1) in BIT-REVERSED order (entry n-1 is zero), the order pk.G1.Z uses. */
+int g16_compute_h(g16_ctx* ctx, const uint8_t* abc_be, unsigned logn, size_t nproofs, uint8_t* h_be);
+/* device variant: d_abc = nproofs * 3n Fr (Montgomery limbs); H overwrites the first vector of
+ * every triple. */
+int g16_compute_h_dev(g16_ctx* ctx, void* d_abc, unsigned logn, size_t nproofs);
+
 /* ---- circuits and proofs ---------------------------------------------------------------- */
 /* Parse a gnark v0.14 R1CS (.ccs) and proving key (.pk), upload and expand the key.
  * acir_json may be NULL: the .ccs `Public`/`Secret` name lists carry the witness mapping. */

@@ -298,3 +298,20 @@ def _ntt_rec(a, w):
 
 def to_mont(x, m): return (x * MONT_R) % m
 def from_mont(x, m): return (x * inv(MONT_R, m)) % m
+
+
+# --- Groth16 quotient (gnark backend/groth16/bn254/prove.go `computeH`) ----
+def quotient_h(a, b, c):
+    """H = (A*B - C) / (X^n - 1) where A,B,C interpolate the rows a,b,c on the size-n domain.
+
+    Returns the n coefficients of H in NATURAL order (coefficient n-1 is always zero).
+    Restated from the definition: evaluate on the coset g*H, divide by the constant
+    Z(g w^k) = g^n - 1, interpolate back.
+    """
+    n = len(a)
+    ea = ntt_natural(ntt_natural(a, inverse=True), coset=COSET_GEN)
+    eb = ntt_natural(ntt_natural(b, inverse=True), coset=COSET_GEN)
+    ec = ntt_natural(ntt_natural(c, inverse=True), coset=COSET_GEN)
+    den = inv(pow(COSET_GEN, n, R) - 1, R)
+    eh = [(x * y - z) * den % R for x, y, z in zip(ea, eb, ec)]
+    return ntt_natural(eh, inverse=True, coset=COSET_GEN)

@@ -34,6 +34,13 @@ PROTOTYPES = {
                                   ctypes.c_char_p]),
     "g16_generate_points": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_size_t,
                                            ctypes.c_char_p]),
+    "g16_ntt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint, ctypes.c_size_t, ctypes.c_int,
+                               ctypes.c_int]),
+    "g16_ntt_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint, ctypes.c_size_t, ctypes.c_int,
+                                   ctypes.c_int]),
+    "g16_compute_h": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint, ctypes.c_size_t,
+                                     ctypes.c_char_p]),
+    "g16_compute_h_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint, ctypes.c_size_t]),
     "g16_msm_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                    ctypes.c_size_t, ctypes.c_void_p]),
 }

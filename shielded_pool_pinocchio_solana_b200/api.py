@@ -51,6 +51,26 @@ class Context:
         check(self.lib.g16_generate_points(self.handle, 0 if group == "g1" else 1, seed, n, out))
         return out.raw
 
+    def ntt(self, values_be: bytes, logn, batch=1, inverse=False, coset=False) -> bytes:
+        """Fr NTT on host buffers: forward = natural -> bit-reversed (DIF), inverse = bit-reversed ->
+        natural (DIT, scaled by 1/n); coset=True shifts by g = 5 (fr/fft OnCoset)."""
+        assert len(values_be) == batch * (32 << logn)
+        buf = ctypes.create_string_buffer(values_be, len(values_be))
+        check(self.lib.g16_ntt(self.handle, buf, logn, batch, int(inverse), int(coset)))
+        return buf.raw
+
+    def ntt_dev(self, d_ptr, logn, batch=1, inverse=False, coset=False):
+        check(self.lib.g16_ntt_dev(self.handle, ctypes.c_void_p(d_ptr), logn, batch, int(inverse), int(coset)))
+
+    def compute_h(self, abc_be: bytes, logn, nproofs=1) -> bytes:
+        assert len(abc_be) == nproofs * 3 * (32 << logn)
+        out = ctypes.create_string_buffer(nproofs * (32 << logn))
+        check(self.lib.g16_compute_h(self.handle, abc_be, logn, nproofs, out))
+        return out.raw
+
+    def compute_h_dev(self, d_abc_ptr, logn, nproofs=1):
+        check(self.lib.g16_compute_h_dev(self.handle, ctypes.c_void_p(d_abc_ptr), logn, nproofs))
+
     def load_bases(self, points_be: bytes, group="g1", window=0, batch_hint=1):
         return Bases(self, points_be, group, window, batch_hint)
 

@@ -150,6 +150,7 @@ void g16_shutdown(g16_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->g1.release();
     ctx->g2.release();
+    ctx->ntt.release();
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -291,6 +292,88 @@ int g16_msm_g1(g16_ctx* ctx, const g16_bases* bases, const uint8_t* scalars_be, 
 }
 int g16_msm_g2(g16_ctx* ctx, const g16_bases* bases, const uint8_t* scalars_be, size_t batch, uint8_t* out_be) {
     return msm_host(ctx, bases, scalars_be, batch, out_be, 1);
+}
+
+// ---- NTT / quotient ---------------------------------------------------------------------------------
+static __global__ void k_fr_to_mont(Fr* v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = v[i].to_mont();
+}
+static __global__ void k_fr_from_mont(Fr* v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = v[i].from_mont();
+}
+
+int g16_ntt_dev(g16_ctx* ctx, void* d_values, unsigned logn, size_t batch, int inverse, int coset) {
+    if (!ctx || !d_values) return G16_E_ARG;
+    G16_CUDA(cudaSetDevice(ctx->device));
+    const NttDomain* d;
+    G16_TRY(ctx->ntt.domain(logn, ctx->stream, &d));
+    ctx->ntt.launches = 0;
+    int rc;
+    if (!inverse)
+        rc = ctx->ntt.run((Fr*)d_values, logn, batch, NTT_DIF, false, coset ? d->coset_nat : nullptr, nullptr,
+                          ctx->stream);
+    else
+        rc = ctx->ntt.run((Fr*)d_values, logn, batch, NTT_DIT, true, nullptr, coset ? d->cosetinv_nat : d->ninv_const,
+                          ctx->stream);
+    ctx->last_launches = ctx->ntt.launches;
+    return rc;
+}
+
+// host buffers (big-endian canonical) -> device Montgomery limbs in ctx->scalars
+static int upload_fr(g16_ctx* ctx, const uint8_t* be, size_t count) {
+    std::vector<Fr> tmp(count);
+    for (size_t i = 0; i < count; i++) be32_to_limbs(be + 32 * i, tmp[i].v);
+    G16_TRY(ctx->scalars.ensure(sizeof(Fr) * count));
+    G16_CUDA(cudaMemcpyAsync(ctx->scalars.ptr, tmp.data(), sizeof(Fr) * count, cudaMemcpyHostToDevice, ctx->stream));
+    k_fr_to_mont<<<cdiv(count, 256), 256, 0, ctx->stream>>>((Fr*)ctx->scalars.ptr, count);
+    G16_CUDA(cudaStreamSynchronize(ctx->stream));  // tmp goes out of scope
+    return G16_OK;
+}
+static int download_fr(g16_ctx* ctx, Fr* d_src, size_t vec_len, size_t vec_stride, size_t nvec, uint8_t* be) {
+    std::vector<Fr> tmp(vec_len * nvec);
+    for (size_t v = 0; v < nvec; v++) {
+        k_fr_from_mont<<<cdiv(vec_len, 256), 256, 0, ctx->stream>>>(d_src + v * vec_stride, vec_len);
+        G16_CUDA(cudaMemcpyAsync(tmp.data() + v * vec_len, d_src + v * vec_stride, sizeof(Fr) * vec_len,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    G16_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < tmp.size(); i++) limbs_to_be32(tmp[i].v, be + 32 * i);
+    return G16_OK;
+}
+
+int g16_ntt(g16_ctx* ctx, uint8_t* values_be, unsigned logn, size_t batch, int inverse, int coset) {
+    if (!ctx || !values_be || logn < 1 || logn > 28) {
+        set_error("g16_ntt: bad arguments");
+        return G16_E_ARG;
+    }
+    G16_CUDA(cudaSetDevice(ctx->device));
+    size_t n = (size_t)1 << logn;
+    G16_TRY(upload_fr(ctx, values_be, n * batch));
+    G16_TRY(g16_ntt_dev(ctx, ctx->scalars.ptr, logn, batch, inverse, coset));
+    return download_fr(ctx, (Fr*)ctx->scalars.ptr, n * batch, n * batch, 1, values_be);
+}
+
+int g16_compute_h_dev(g16_ctx* ctx, void* d_abc, unsigned logn, size_t nproofs) {
+    if (!ctx || !d_abc) return G16_E_ARG;
+    G16_CUDA(cudaSetDevice(ctx->device));
+    ctx->ntt.launches = 0;
+    int rc = ctx->ntt.compute_h((Fr*)d_abc, logn, nproofs, ctx->stream);
+    ctx->last_launches = ctx->ntt.launches;
+    return rc;
+}
+
+int g16_compute_h(g16_ctx* ctx, const uint8_t* abc_be, unsigned logn, size_t nproofs, uint8_t* h_be) {
+    if (!ctx || !abc_be || !h_be || logn < 1 || logn > 28) {
+        set_error("g16_compute_h: bad arguments");
+        return G16_E_ARG;
+    }
+    G16_CUDA(cudaSetDevice(ctx->device));
+    size_t n = (size_t)1 << logn;
+    G16_TRY(upload_fr(ctx, abc_be, 3 * n * nproofs));
+    G16_TRY(g16_compute_h_dev(ctx, ctx->scalars.ptr, logn, nproofs));
+    return download_fr(ctx, (Fr*)ctx->scalars.ptr, n, 3 * n, nproofs, h_be);
 }
 
 }  // extern "C"

@@ -3,6 +3,7 @@
 #include "../../include/g16b200.h"
 #include "common.cuh"
 #include "msm.cuh"
+#include "ntt.cuh"
 
 namespace g16 {
 
@@ -30,6 +31,7 @@ struct g16_ctx {
     int last_launches = 0;
     g16::MsmRunner<g16::Fp> g1;
     g16::MsmRunner<g16::Fp2> g2;
+    g16::NttEngine ntt;
     g16::DeviceBuf scratch, scalars, results;
 };
 

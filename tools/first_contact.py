@@ -15,7 +15,10 @@ for grp in ("g1", "g2"):
     got = b.msm(bytes.fromhex(c["scalars"]), batch=c["batch"])
     print(grp, "golden parity:", got.hex() == c["results"], "window", b.window, flush=True)
 
-ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+ctx.set_stream(stream.cuda_stream)
+assert stream.cuda_stream != 0
 def time_msm(logn, batch, group="g1", reps=5):
     n = 1 << logn
     t0 = time.time()
@@ -44,3 +47,21 @@ for logn, batch in ((14, 1), (14, 64), (16, 1), (18, 1), (20, 1), (22, 1)):
     time_msm(logn, batch)
 time_msm(14, 16, "g2")
 time_msm(18, 1, "g2")
+
+def time_ntt(logn, batch, reps=5):
+    n = 1 << logn
+    x = torch.randint(0, 2**31 - 1, (batch * n, 8), dtype=torch.int32, device="cuda")
+    x[:, 7] &= 0x0fffffff
+    for _ in range(2):
+        ctx.ntt_dev(x.data_ptr(), logn, batch)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(reps):
+        ctx.ntt_dev(x.data_ptr(), logn, batch)
+    ev[1].record(); torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / reps
+    bf = batch * (n // 2) * logn
+    print(f"ntt n=2^{logn} batch={batch}: {ms:.3f} ms  {bf/ms/1e6:.2f} G butterflies/s  {batch*n*64*ctx.last_launches()/ms/1e6:.0f} GB/s", flush=True)
+for logn, batch in ((14, 192), (15, 96), (18, 8), (20, 4), (22, 1), (24, 1)):
+    time_ntt(logn, batch)
