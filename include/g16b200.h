@@ -111,7 +111,8 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
                      const char* acir_json, g16_circuit** out);
 void g16_circuit_free(g16_circuit* c);
 /* sizes: what[0]=nbConstraints [1]=nbWires [2]=nbPublic(incl. ONE) [3]=nbSecret [4]=domain size
- *        [5]=nbCommitments [6..10] = MSM sizes A,B,K,Z,commit */
+ *        [5]=nbCommitments [6..10] = MSM sizes A,B,K,Z,commit [11]=max proofs per device batch
+ *        [12..15] = window bits chosen for the A, B1, K+Z and B2 MSMs */
 int g16_circuit_info(const g16_circuit* c, uint64_t what[16]);
 
 /* One proof from a Noir witness (`target/<name>.gz`, as written by `nargo execute`).
@@ -133,9 +134,16 @@ int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, siz
  * valid proof is wanted; for throughput runs any vector does identical work. */
 int g16_prove_wires(g16_circuit* c, size_t n, const uint8_t* wires_be, const uint8_t* rnd, uint8_t* proofs);
 /* Device-resident throughput path: d_wires = n * nbWires Fr in Montgomery limb form already in
- * HBM; d_proof_points receives per proof 5 affine results (Ar, Bs1, Krs-partial, PoK in G1 and
- * Bs in G2) in Montgomery limb form.  Asynchronous. */
+ * HBM (n <= max_batch, g16_circuit_info what[11]); r = s = 0.  d_proof_points receives per proof
+ * 320 bytes: Ar (G1) | Bs (G2) | Krs (G1) | PoK (G1), affine, canonical little-endian limbs.
+ * Asynchronous on the context stream. */
 int g16_prove_wires_dev(g16_circuit* c, size_t n, const void* d_wires, void* d_proof_points);
+/* Solver only (no GPU): extend an assignment to the full wire vector (nbWires * 32 B BE).
+ * challenges_be: the BSB22 challenge of each commitment, supplied by the caller;
+ * committed_be (optional): receives the committed values of the first commitment. */
+int g16_solve_assignment(const uint8_t* ccs, size_t ccs_len, const uint8_t* assignment_be, size_t n_values,
+                         const uint8_t* blinder_be, const uint8_t* challenges_be, size_t n_challenges,
+                         uint8_t* wires_be, size_t wires_cap, uint8_t* committed_be, size_t committed_cap);
 
 #ifdef __cplusplus
 }

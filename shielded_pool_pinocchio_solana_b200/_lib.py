@@ -43,6 +43,23 @@ PROTOTYPES = {
     "g16_compute_h_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint, ctypes.c_size_t]),
     "g16_msm_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                    ctypes.c_size_t, ctypes.c_void_p]),
+    "g16_circuit_load": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p,
+                                        ctypes.c_size_t, ctypes.c_char_p, c_void_pp]),
+    "g16_circuit_free": (None, [ctypes.c_void_p]),
+    "g16_circuit_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]),
+    "g16_prove": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_char_p,
+                                 ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t)]),
+    "g16_prove_assignment": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p,
+                                            ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p,
+                                            ctypes.POINTER(ctypes.c_size_t)]),
+    "g16_prove_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
+                                       ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]),
+    "g16_prove_wires": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_char_p,
+                                       ctypes.c_char_p]),
+    "g16_prove_wires_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
+    "g16_solve_assignment": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
+                                            ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p,
+                                            ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]),
 }
 
 _lib = None

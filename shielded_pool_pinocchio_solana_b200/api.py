@@ -108,3 +108,70 @@ class Bases:
     def msm_dev(self, d_scalars_ptr, batch, d_out_ptr, montgomery=True):
         check(self.ctx.lib.g16_msm_dev(self.ctx.handle, self.handle, ctypes.c_void_p(d_scalars_ptr),
                                        1 if montgomery else 0, batch, ctypes.c_void_p(d_out_ptr)))
+
+
+class Circuit:
+    """A constraint system + proving key resident on one GPU (parsed and uploaded once)."""
+
+    INFO = ("nb_constraints", "nb_wires", "nb_public", "nb_secret", "domain", "nb_commitments", "n_a", "n_b", "n_k",
+            "n_z", "n_committed", "max_batch", "window_a", "window_b1", "window_kz", "window_b2")
+
+    def __init__(self, ctx, ccs: bytes, pk: bytes, acir_json=None):
+        self.ctx = ctx
+        self.handle = ctypes.c_void_p()
+        check(ctx.lib.g16_circuit_load(ctx.handle, ccs, len(ccs), pk, len(pk), acir_json, ctypes.byref(self.handle)))
+        arr = (ctypes.c_uint64 * 16)()
+        check(ctx.lib.g16_circuit_info(self.handle, arr))
+        self.info = dict(zip(self.INFO, [int(x) for x in arr]))
+        self.proof_len = 388 if self.info["nb_commitments"] else 324
+        self.pw_len = 12 + 32 * (self.info["nb_public"] - 1)
+        self.n_values = self.info["nb_public"] - 1 + self.info["nb_secret"]
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.g16_circuit_free(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def prove_batch(self, assignments_be: bytes, n, rnd: bytes = None):
+        """n proofs from n assignments (public then secret values, 32 B BE each).
+        -> (list of proof bytes, list of public-witness bytes)."""
+        assert len(assignments_be) == n * self.n_values * 32
+        assert rnd is None or len(rnd) == 96 * n
+        proofs = ctypes.create_string_buffer(n * self.proof_len)
+        pws = ctypes.create_string_buffer(n * self.pw_len)
+        check(self.ctx.lib.g16_prove_batch(self.handle, n, assignments_be, self.n_values, rnd, proofs, pws, self.pw_len))
+        P, W = proofs.raw, pws.raw
+        return ([P[i * self.proof_len:(i + 1) * self.proof_len] for i in range(n)],
+                [W[i * self.pw_len:(i + 1) * self.pw_len] for i in range(n)])
+
+    def prove_assignment(self, assignment_be: bytes, rnd: bytes = None):
+        p, w = self.prove_batch(assignment_be, 1, rnd)
+        return p[0], w[0]
+
+    def prove(self, witness_gz: bytes, rnd: bytes = None):
+        """Drop-in for `sunspot prove`: Noir witness (.gz) in, (proof, public witness) bytes out."""
+        proof = ctypes.create_string_buffer(self.proof_len)
+        pw = ctypes.create_string_buffer(self.pw_len)
+        pl, wl = ctypes.c_size_t(self.proof_len), ctypes.c_size_t(self.pw_len)
+        check(self.ctx.lib.g16_prove(self.handle, witness_gz, len(witness_gz), rnd, proof, ctypes.byref(pl), pw,
+                                     ctypes.byref(wl)))
+        return proof.raw[:pl.value], pw.raw[:wl.value]
+
+    def prove_wires(self, wires_be: bytes, n, rnd: bytes = None):
+        assert len(wires_be) == n * self.info["nb_wires"] * 32
+        proofs = ctypes.create_string_buffer(n * self.proof_len)
+        check(self.ctx.lib.g16_prove_wires(self.handle, n, wires_be, rnd, proofs))
+        return [proofs.raw[i * self.proof_len:(i + 1) * self.proof_len] for i in range(n)]
+
+    def prove_wires_dev(self, d_wires_ptr, n, d_out_ptr):
+        check(self.ctx.lib.g16_prove_wires_dev(self.handle, n, ctypes.c_void_p(d_wires_ptr), ctypes.c_void_p(d_out_ptr)))
+
+
+def solve_assignment(ccs: bytes, assignment_be: bytes, nb_wires, blinder_be=None, challenges_be=b"", n_committed=0):
+    """Host-only witness solver (no GPU): -> (wires_be, committed_be)."""
+    lib = _lib.load()
+    wires = ctypes.create_string_buffer(nb_wires * 32)
+    committed = ctypes.create_string_buffer(max(1, n_committed) * 32)
+    check(lib.g16_solve_assignment(ccs, len(ccs), assignment_be, len(assignment_be) // 32, blinder_be, challenges_be,
+                                   len(challenges_be) // 32, wires, len(wires), committed, n_committed * 32))
+    return wires.raw, committed.raw[:n_committed * 32]

@@ -109,7 +109,8 @@ int MsmRunner<F>::reserve(const MsmBases<F>& bases, size_t batch) {
 
 template <class F>
 int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stride, const uint32_t* d_map,
-                      int montgomery, size_t batch, Affine<F>* d_out, cudaStream_t st) {
+                      int montgomery, size_t batch, Affine<F>* d_out, cudaStream_t st, const Fr* d_scalars1,
+                      size_t stride1) {
     launches = 0;
     if (batch == 0) return G16_OK;
     if (!bases.table) {
@@ -124,11 +125,13 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     dim3 dgrid(cdiv(n, MSM_DIGIT_THREADS), (unsigned)batch);
 
     G16_CUDA(cudaMemsetAsync(counts, 0, 4 * nbuckets, st));
-    k_msm_digits<0><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_map, n, montgomery, cfg, counts, nullptr);
+    k_msm_digits<0><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery, cfg,
+                                                         counts, nullptr);
     k_scan_tile_sums<<<ntiles, SCAN_THREADS, 0, st>>>(counts, nbuckets, tile_sums);
     k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(tile_sums, ntiles);
     k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts, nbuckets, tile_sums, starts, counts);
-    k_msm_digits<1><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_map, n, montgomery, cfg, counts, entries);
+    k_msm_digits<1><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery, cfg,
+                                                         counts, entries);
     // after the scatter, counts[k] (the cursor) is the END of bucket k
     k_msm_accumulate<F><<<cdiv(nbuckets, 128), 128, 0, st>>>(bases.table, entries, starts, counts, buckets,
                                                              (uint32_t)nbuckets);

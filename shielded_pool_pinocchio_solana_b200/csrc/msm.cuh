@@ -83,15 +83,18 @@ constexpr int MSM_DIGIT_THREADS = 256;
 // pass 0: count  /  pass 1: scatter.   grid = (ceil(n/256), batch)
 template <int PASS>
 __global__ void __launch_bounds__(MSM_DIGIT_THREADS)
-k_msm_digits(const Fr* __restrict__ scalars, size_t scalar_stride, const uint32_t* __restrict__ map, uint32_t n,
+k_msm_digits(const Fr* __restrict__ scalars, size_t scalar_stride, const Fr* __restrict__ scalars1,
+             size_t scalar_stride1, const uint32_t* __restrict__ map, uint32_t n,
              int montgomery, MsmConfig cfg, uint32_t* __restrict__ counts_or_cursor,
              uint32_t* __restrict__ entries) {
     __shared__ uint32_t sk[8][MSM_DIGIT_THREADS];
     uint32_t i = blockIdx.x * MSM_DIGIT_THREADS + threadIdx.x;
     uint32_t b = blockIdx.y;
     if (i >= n) return;
+    // map entries with bit 31 set read the second scalar source (e.g. the quotient H next to the wires)
     uint32_t si = map ? map[i] : i;
-    Fr k = scalars[(size_t)b * scalar_stride + si];
+    Fr k = (si >> 31) ? scalars1[(size_t)b * scalar_stride1 + (si & 0x7fffffffu)]
+                      : scalars[(size_t)b * scalar_stride + si];
     if (montgomery) k = k.from_mont();
 #pragma unroll
     for (int l = 0; l < 8; l++) sk[l][threadIdx.x] = k.v[l];
@@ -366,7 +369,7 @@ class MsmRunner {
     // Computes out[b] = sum_i scalars[b*stride + map[i]] * P_i  for b < batch.  `out` is a DEVICE
     // array of `batch` affine points (Montgomery).  All work is enqueued on `st`.
     int run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stride, const uint32_t* d_map, int montgomery,
-            size_t batch, Affine<F>* d_out, cudaStream_t st);
+            size_t batch, Affine<F>* d_out, cudaStream_t st, const Fr* d_scalars1 = nullptr, size_t stride1 = 0);
     void release();
     // kernels launched by the last run() (for bench.py's gpu_launches)
     int launches = 0;

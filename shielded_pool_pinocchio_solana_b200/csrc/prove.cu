@@ -1,0 +1,755 @@
+// prove.cu -- circuit handle + batched Groth16 proving pipeline behind g16_circuit_load /
+// g16_prove* (include/g16b200.h).  See prove.cuh for what it replaces.
+//
+// Per batch of B proofs of one circuit (everything enqueued on the context stream):
+//   host   : solve phase 1 (threads)                 -> committed values
+//   device : commitment MSM  (B x 490 points)        -> D2H 64 B per proof
+//   host   : hash_to_field challenge, solve phase 2  -> full wire vectors (Montgomery), H2D
+//   device : R1CS SpMV  a,b,c = A.w, B.w, C.w        (k_r1cs_spmv)
+//            quotient H                              (ntt.cu: 7 transforms, batched)
+//            MSMs  A | B1 | B2 (G2) | K+Z | PoK      (msm.cu; alpha/beta/delta terms ride along as
+//                                                     extra bases with scalars 1, r, s, -rs)
+//            finalize: Krs += s*Ar + r*Bs1, out of Montgomery form
+//   host   : gnark raw serialisation (388-byte proof, public witness)
+#include "prove.cuh"
+
+#include <string.h>
+
+#include <atomic>
+#include <fstream>
+#include <thread>
+
+#include "hostutil.hpp"
+
+namespace g16 {
+
+// ------------------------------------------------------------------------------------------------
+// proving-key file (gnark ProvingKey.WriteRawTo / WriteTo; layout per SURVEY.md 9.2, UNVERIFIED
+// against a real gnark .pk -- none exists in the reference tree)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct PkReader {
+    const uint8_t* p;
+    size_t len, off = 0;
+    bool ok = true;
+    bool need(size_t n) {
+        if (off + n > len) ok = false;
+        return ok;
+    }
+    uint32_t u32() {
+        if (!need(4)) return 0;
+        uint32_t v = ((uint32_t)p[off] << 24) | ((uint32_t)p[off + 1] << 16) | ((uint32_t)p[off + 2] << 8) | p[off + 3];
+        off += 4;
+        return v;
+    }
+    uint64_t u64() {
+        uint64_t hi = u32();
+        return (hi << 32) | u32();
+    }
+    bool g1(G1Affine* o) {
+        if (!need(64)) return false;
+        if ((p[off] & 0xc0) == 0x80 || (p[off] & 0xc0) == 0xc0) {  // compressed encodings
+            ok = false;
+            return false;
+        }
+        g1_from_be(p + off, o);
+        off += 64;
+        return true;
+    }
+    bool g2(G2Affine* o) {
+        if (!need(128)) return false;
+        if ((p[off] & 0xc0) == 0x80 || (p[off] & 0xc0) == 0xc0) {
+            ok = false;
+            return false;
+        }
+        g2_from_be(p + off, o);
+        off += 128;
+        return true;
+    }
+    bool g1s(std::vector<G1Affine>* v) {
+        uint32_t n = u32();
+        if (!ok || (size_t)n * 64 > len - off) return ok = false;
+        v->resize(n);
+        for (auto& x : *v)
+            if (!g1(&x)) return false;
+        return true;
+    }
+    bool g2s(std::vector<G2Affine>* v) {
+        uint32_t n = u32();
+        if (!ok || (size_t)n * 128 > len - off) return ok = false;
+        v->resize(n);
+        for (auto& x : *v)
+            if (!g2(&x)) return false;
+        return true;
+    }
+    bool bools(std::vector<uint8_t>* v) {
+        uint32_t n = u32();
+        if (!ok || n > len - off) return ok = false;
+        v->assign(p + off, p + off + n);
+        off += n;
+        return true;
+    }
+};
+}  // namespace
+
+int parse_pk(const uint8_t* buf, size_t len, ProvingKeyHost* out) {
+    // The fft.Domain header is 8 + 5*32 bytes, optionally followed by a 1-byte `withPrecompute`
+    // flag (newer gnark-crypto).  Try both and keep the one that consumes the file exactly.
+    for (int flag_byte = 1; flag_byte >= 0; flag_byte--) {
+        PkReader r{buf, len};
+        ProvingKeyHost pk;
+        pk.domain = r.u64();
+        r.need(5 * 32 + flag_byte);
+        if (!r.ok) continue;
+        r.off += 5 * 32 + flag_byte;
+        r.g1(&pk.alpha1); r.g1(&pk.beta1); r.g1(&pk.delta1);
+        r.g1s(&pk.A); r.g1s(&pk.B1); r.g1s(&pk.Z); r.g1s(&pk.K);
+        r.g2(&pk.beta2); r.g2(&pk.delta2); r.g2s(&pk.B2);
+        if (!r.ok) continue;
+        uint64_t nw = r.u64(), ninf_a = r.u64(), ninf_b = r.u64();
+        r.bools(&pk.infinity_a);
+        r.bools(&pk.infinity_b);
+        if (!r.ok || pk.infinity_a.size() != nw || pk.infinity_b.size() != nw) continue;
+        uint64_t ca = 0, cb = 0;
+        for (auto v : pk.infinity_a) ca += v != 0;
+        for (auto v : pk.infinity_b) cb += v != 0;
+        if (ca != ninf_a || cb != ninf_b || pk.A.size() != nw - ninf_a || pk.B1.size() != nw - ninf_b ||
+            pk.B2.size() != pk.B1.size())
+            continue;
+        uint32_t nkeys = r.u32();
+        if (!r.ok || nkeys > 64) continue;
+        pk.commitment_keys.resize(nkeys);
+        for (auto& k : pk.commitment_keys) {
+            r.g1s(&k.basis);
+            r.g1s(&k.basis_exp_sigma);
+            if (r.ok && k.basis.size() != k.basis_exp_sigma.size()) r.ok = false;
+        }
+        if (!r.ok || r.off != len) continue;
+        if (pk.domain == 0 || (pk.domain & (pk.domain - 1))) continue;
+        *out = std::move(pk);
+        return G16_OK;
+    }
+    set_error("parse_pk: not a raw (uncompressed) gnark groth16 proving key for BN254");
+    return G16_E_PARSE;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+// One thread per (proof, matrix, row): abc[proof][matrix][row] = sum coeff * w[wire].
+// Rows >= nb_constraints are the zero padding of the FFT domain.
+__global__ void __launch_bounds__(256)
+k_r1cs_spmv(const uint32_t* __restrict__ rp0, const uint32_t* __restrict__ cid0, const uint32_t* __restrict__ wid0,
+            const uint32_t* __restrict__ rp1, const uint32_t* __restrict__ cid1, const uint32_t* __restrict__ wid1,
+            const uint32_t* __restrict__ rp2, const uint32_t* __restrict__ cid2, const uint32_t* __restrict__ wid2,
+            const Fr* __restrict__ coeffs, const Fr* __restrict__ wires, size_t wstride, Fr* __restrict__ abc,
+            uint32_t nrows, uint32_t n, int unit_ids) {
+    uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t m = blockIdx.y, proof = blockIdx.z;
+    if (row >= n) return;
+    Fr acc = Fr::zero();
+    if (row < nrows) {
+        const uint32_t* rp = m == 0 ? rp0 : (m == 1 ? rp1 : rp2);
+        const uint32_t* cid = m == 0 ? cid0 : (m == 1 ? cid1 : cid2);
+        const uint32_t* wid = m == 0 ? wid0 : (m == 1 ? wid1 : wid2);
+        const Fr* w = wires + (size_t)proof * wstride;
+        for (uint32_t k = rp[row], e = rp[row + 1]; k < e; k++) {
+            uint32_t c = cid[k];
+            Fr x = w[wid[k]];
+            // gnark's coefficient table starts 0, 1, 2, -1, -2 (checked at load -> unit_ids): skip
+            // the multiplication for the +-1 entries that make up most real circuits
+            if (unit_ids && c == 1) acc = acc + x;
+            else if (unit_ids && c == 3) acc = acc - x;
+            else if (!(unit_ids && c == 0)) acc = acc + coeffs[c] * x;
+        }
+    }
+    abc[((size_t)proof * 3 + m) * n + row] = acc;
+}
+
+__global__ void k_set_one(Fr* wires, size_t wstride, size_t slot, uint32_t n) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n) wires[(size_t)b * wstride + slot] = Fr::one();
+}
+
+// [k]P for a 256-bit canonical scalar, affine base (double-and-add, MSB first)
+__device__ G1XYZZ g1_scalar_mul(const G1Affine& p, const Fr& k) {
+    G1XYZZ acc = G1XYZZ::inf();
+    bool started = false;
+    for (int bit = 253; bit >= 0; bit--) {
+        if (started) acc = acc.dbl();
+        if ((k.v[bit >> 5] >> (bit & 31)) & 1u) {
+            acc.madd(p);
+            started = true;
+        }
+    }
+    return acc;
+}
+
+// One 32-thread CTA per proof: lanes 0/1 compute s*Ar and r*Bs1, lane 0 assembles Krs; lanes 0..3
+// convert the four outputs out of Montgomery form.
+__global__ void __launch_bounds__(32)
+k_finalize(const G1Affine* __restrict__ ar, const G1Affine* __restrict__ bs1, const G2Affine* __restrict__ bs2,
+           const G1Affine* __restrict__ kz, const G1Affine* __restrict__ pok, const Fr* __restrict__ wires,
+           size_t wstride, size_t nw, ProofPoints* __restrict__ out) {
+    __shared__ G1XYZZ part[2];
+    uint32_t b = blockIdx.x, t = threadIdx.x;
+    const Fr* x = wires + (size_t)b * wstride + nw;
+    if (t < 2) {
+        Fr k = (t == 0 ? x[X_S] : x[X_R]).from_mont();
+        part[t] = g1_scalar_mul(t == 0 ? ar[b] : bs1[b], k);
+    }
+    __syncthreads();
+    auto unmont1 = [](G1Affine p) {
+        p.x = p.x.from_mont();
+        p.y = p.y.from_mont();
+        return p;
+    };
+    if (t == 0) {
+        G1XYZZ acc = part[0];
+        acc.add(part[1]);
+        acc.madd(kz[b]);
+        out[b].krs = unmont1(acc.to_affine());
+    } else if (t == 1) {
+        out[b].ar = unmont1(ar[b]);
+    } else if (t == 2) {
+        G2Affine q = bs2[b];
+        q.x.c0 = q.x.c0.from_mont(); q.x.c1 = q.x.c1.from_mont();
+        q.y.c0 = q.y.c0.from_mont(); q.y.c1 = q.y.c1.from_mont();
+        out[b].bs = q;
+    } else if (t == 3) {
+        out[b].pok = unmont1(pok[b]);
+    }
+}
+
+}  // namespace g16
+
+using namespace g16;
+
+g16_circuit::~g16_circuit() {
+    if (ctx) cudaSetDevice(ctx->device);
+    for (int m = 0; m < 3; m++) {
+        cudaFree(d_rowptr[m]); cudaFree(d_cid[m]); cudaFree(d_wid[m]);
+    }
+    cudaFree(d_coeffs);
+    cudaFree(d_mapA); cudaFree(d_mapB); cudaFree(d_mapKZ); cudaFree(d_mapPok);
+    cudaFree(d_tmp_g1); cudaFree(d_tmp_g2);
+    if (h_pinned) cudaFreeHost(h_pinned);
+}
+
+namespace {
+
+template <class T>
+int upload_vec(const std::vector<T>& v, T** d, cudaStream_t st) {
+    G16_CUDA(cudaMalloc(d, sizeof(T) * (v.size() ? v.size() : 1)));
+    if (!v.empty()) G16_CUDA(cudaMemcpyAsync(*d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, st));
+    return G16_OK;
+}
+
+int random_fr(HFr* out) {
+    std::ifstream ur("/dev/urandom", std::ios::binary);
+    for (int tries = 0; tries < 64; tries++) {
+        uint8_t b[32];
+        ur.read((char*)b, 32);
+        if (!ur) break;
+        b[0] &= 0x3f;
+        uint64_t l[4];
+        for (int i = 0; i < 4; i++) {
+            uint64_t v = 0;
+            for (int k = 0; k < 8; k++) v = (v << 8) | b[(3 - i) * 8 + k];
+            l[i] = v;
+        }
+        if (!HFr::geq_mod(l)) {
+            *out = HFr::from_be(b);
+            return G16_OK;
+        }
+    }
+    set_error("could not read /dev/urandom");
+    return G16_E_INTERNAL;
+}
+
+size_t default_threads() {
+    unsigned hc = std::thread::hardware_concurrency();
+    return hc ? hc : 4;
+}
+
+template <class Fn>
+void parallel_for(size_t n, Fn fn) {
+    size_t nt = std::min(default_threads(), n);
+    if (nt <= 1) {
+        for (size_t i = 0; i < n; i++) fn(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++)
+        th.emplace_back([&] {
+            for (size_t i; (i = next.fetch_add(1)) < n;) fn(i);
+        });
+    for (auto& x : th) x.join();
+}
+
+// Device part of the pipeline: wires (with the X_* slots filled) are already in c->d_wires.
+int prove_device(g16_circuit* c, size_t B) {
+    g16_ctx* ctx = c->ctx;
+    cudaStream_t st = ctx->stream;
+    const Fr* W = (const Fr*)c->d_wires.ptr;
+    Fr* abc = (Fr*)c->d_abc.ptr;
+    int launches = 0;
+    dim3 grid(cdiv(c->n, 256), 3, (unsigned)B);
+    k_r1cs_spmv<<<grid, 256, 0, st>>>(c->d_rowptr[0], c->d_cid[0], c->d_wid[0], c->d_rowptr[1], c->d_cid[1],
+                                      c->d_wid[1], c->d_rowptr[2], c->d_cid[2], c->d_wid[2], c->d_coeffs, W,
+                                      c->wstride, abc, c->circ.nb_constraints, (uint32_t)c->n, c->unit_ids);
+    launches++;
+    ctx->ntt.launches = 0;
+    G16_TRY(ctx->ntt.compute_h(abc, c->logn, B, st));
+    launches += ctx->ntt.launches;
+    G1Affine* rA = c->d_tmp_g1;
+    G1Affine* rB1 = c->d_tmp_g1 + c->max_batch;
+    G1Affine* rKZ = c->d_tmp_g1 + 2 * c->max_batch;
+    G1Affine* rPok = c->d_tmp_g1 + 3 * c->max_batch;
+    G16_TRY(ctx->g1.run(c->bA, W, c->wstride, c->d_mapA, 1, B, rA, st));
+    launches += ctx->g1.launches;
+    G16_TRY(ctx->g1.run(c->bB1, W, c->wstride, c->d_mapB, 1, B, rB1, st));
+    launches += ctx->g1.launches;
+    G16_TRY(ctx->g2.run(c->bB2, W, c->wstride, c->d_mapB, 1, B, c->d_tmp_g2, st));
+    launches += ctx->g2.launches;
+    G16_TRY(ctx->g1.run(c->bKZ, W, c->wstride, c->d_mapKZ, 1, B, rKZ, st, abc, 3 * c->n));
+    launches += ctx->g1.launches;
+    if (c->has_commitment) {
+        G16_TRY(ctx->g1.run(c->bPok, W, c->wstride, c->d_mapPok, 1, B, rPok, st));
+        launches += ctx->g1.launches;
+    } else {
+        G16_CUDA(cudaMemsetAsync(rPok, 0, sizeof(G1Affine) * B, st));
+    }
+    k_finalize<<<(unsigned)B, 32, 0, st>>>(rA, rB1, c->d_tmp_g2, rKZ, rPok, W, c->wstride, c->nw,
+                                           (ProofPoints*)c->d_out.ptr);
+    launches++;
+    G16_CUDA(cudaGetLastError());
+    c->last_launches = launches;
+    ctx->last_launches = launches;
+    return G16_OK;
+}
+
+void fill_extras(HFr* w, size_t nw, const HFr& r, const HFr& s) {
+    w[nw + X_ONE] = HFr::one();
+    w[nw + X_R] = r;
+    w[nw + X_S] = s;
+    w[nw + X_NEG_RS] = (r * s).neg();
+    for (int k = X_NEG_RS + 1; k < X_COUNT; k++) w[nw + k] = HFr::zero();
+}
+
+void write_proof_bytes(const ProofPoints& pp, const G1Affine* commitment, uint8_t* out) {
+    g1_to_be(pp.ar, out);
+    g2_to_be(pp.bs, out + 64);
+    g1_to_be(pp.krs, out + 192);
+    out[256] = 0; out[257] = 0; out[258] = 0; out[259] = commitment ? 1 : 0;
+    size_t off = 260;
+    if (commitment) {
+        g1_to_be(*commitment, out + off);
+        off += 64;
+    }
+    g1_to_be(pp.pok, out + off);
+}
+
+}  // namespace
+
+namespace g16 {
+int witness_to_assignment(const Circuit& c, const uint8_t* gz, size_t gz_len, std::vector<uint8_t>* assignment_be);
+}
+
+extern "C" {
+
+int g16_prove_assignment(g16_circuit* c, const uint8_t* assignment_be, size_t n_values, const uint8_t rnd[96],
+                         uint8_t* proof, size_t* proof_len, uint8_t* pw, size_t* pw_len);
+
+int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uint8_t* pk, size_t pk_len,
+                     const char* acir_json, g16_circuit** out) {
+    (void)acir_json;
+    if (!ctx || !ccs || !pk || !out) {
+        set_error("g16_circuit_load: bad arguments");
+        return G16_E_ARG;
+    }
+    G16_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<g16_circuit> c(new g16_circuit());
+    c->ctx = ctx;
+    G16_TRY(parse_ccs(ccs, ccs_len, &c->circ));
+    ProvingKeyHost pkh;
+    G16_TRY(parse_pk(pk, pk_len, &pkh));
+    const Circuit& circ = c->circ;
+    c->logn = circ.log_domain();
+    c->n = (size_t)1 << c->logn;
+    c->nw = circ.nb_wires();
+    c->wstride = c->nw + X_COUNT;
+    if (pkh.domain != c->n || pkh.infinity_a.size() != c->nw) {
+        set_error("g16_circuit_load: proving key does not belong to this constraint system (domain / wire count)");
+        return G16_E_ARG;
+    }
+    if (circ.commitments.size() > 1 || pkh.commitment_keys.size() != circ.commitments.size()) {
+        set_error("g16_circuit_load: circuits with more than one BSB22 commitment are not supported yet");
+        return G16_E_ARG;
+    }
+    if (pkh.Z.size() != c->n - 1 && pkh.Z.size() != c->n) {
+        set_error("g16_circuit_load: pk.G1.Z has an unexpected length");
+        return G16_E_PARSE;
+    }
+    cudaStream_t st = ctx->stream;
+    // ---- scalar maps -------------------------------------------------------------------------
+    const uint32_t X0 = (uint32_t)c->nw;
+    std::vector<uint32_t> mapA, mapB, mapKZ, mapPok;
+    for (uint32_t i = 0; i < c->nw; i++) {
+        if (!pkh.infinity_a[i]) mapA.push_back(i);
+        if (!pkh.infinity_b[i]) mapB.push_back(i);
+    }
+    std::vector<uint8_t> skip(c->nw, 0);
+    for (auto& info : circ.commitments) {
+        skip[info.commitment_index] = 1;
+        for (uint32_t w : info.private_committed) skip[w] = 1;
+    }
+    for (uint32_t i = circ.nb_public; i < c->nw; i++)
+        if (!skip[i]) mapKZ.push_back(i);
+    if (mapKZ.size() != pkh.K.size()) {
+        set_error("g16_circuit_load: pk.G1.K length does not match the private non-committed wires");
+        return G16_E_ARG;
+    }
+    c->nA = mapA.size(); c->nB = mapB.size(); c->nK = pkh.K.size(); c->nZ = c->n - 1;
+    // alpha/beta/delta ride along as extra bases
+    std::vector<G1Affine> basesA = pkh.A, basesB1 = pkh.B1, basesKZ = pkh.K;
+    std::vector<G2Affine> basesB2 = pkh.B2;
+    basesA.push_back(pkh.alpha1); mapA.push_back(X0 + X_ONE);
+    basesA.push_back(pkh.delta1); mapA.push_back(X0 + X_R);
+    basesB1.push_back(pkh.beta1); basesB2.push_back(pkh.beta2); mapB.push_back(X0 + X_ONE);
+    basesB1.push_back(pkh.delta1); basesB2.push_back(pkh.delta2); mapB.push_back(X0 + X_S);
+    for (size_t j = 0; j < c->nZ; j++) {
+        basesKZ.push_back(pkh.Z[j]);
+        mapKZ.push_back(0x80000000u | (uint32_t)j);   // h lives in the first vector of the abc triple
+    }
+    basesKZ.push_back(pkh.delta1); mapKZ.push_back(X0 + X_NEG_RS);
+    c->has_commitment = !circ.commitments.empty();
+    if (c->has_commitment) {
+        c->committed_wires = circ.commitments[0].private_committed;
+        c->n_committed = c->committed_wires.size();
+        if (pkh.commitment_keys[0].basis.size() != c->n_committed) {
+            set_error("g16_circuit_load: commitment key size does not match PrivateCommitted");
+            return G16_E_ARG;
+        }
+        mapPok = c->committed_wires;
+    }
+    // ---- batch size: bounded by scratch memory (entries dominate: 4 B per base, window and proof)
+    size_t max_batch = 64;
+    if (c->n >= (1u << 18)) max_batch = 1;
+    else if (c->n >= (1u << 16)) max_batch = 8;
+    c->max_batch = max_batch;
+    // ---- bases -------------------------------------------------------------------------------
+    auto win = [&](size_t npts) { return msm_pick_window(npts, max_batch); };
+    G16_TRY(c->bA.load(basesA.data(), basesA.size(), win(basesA.size()), 1, st));
+    G16_TRY(c->bB1.load(basesB1.data(), basesB1.size(), win(basesB1.size()), 1, st));
+    G16_TRY(c->bB2.load(basesB2.data(), basesB2.size(), win(basesB2.size()), 1, st));
+    G16_TRY(c->bKZ.load(basesKZ.data(), basesKZ.size(), win(basesKZ.size()), 1, st));
+    if (c->has_commitment) {
+        auto& key = pkh.commitment_keys[0];
+        G16_TRY(c->bCommit.load(key.basis.data(), key.basis.size(), win(key.basis.size()), 1, st));
+        G16_TRY(c->bPok.load(key.basis_exp_sigma.data(), key.basis_exp_sigma.size(), win(key.basis.size()), 1, st));
+    }
+    G16_TRY(upload_vec(mapA, &c->d_mapA, st));
+    G16_TRY(upload_vec(mapB, &c->d_mapB, st));
+    G16_TRY(upload_vec(mapKZ, &c->d_mapKZ, st));
+    G16_TRY(upload_vec(mapPok, &c->d_mapPok, st));
+    // ---- R1CS ----------------------------------------------------------------------------------
+    const Circuit::Csr* M[3] = {&circ.A, &circ.B, &circ.C};
+    for (int m = 0; m < 3; m++) {
+        G16_TRY(upload_vec(M[m]->rowptr, &c->d_rowptr[m], st));
+        G16_TRY(upload_vec(M[m]->coeff, &c->d_cid[m], st));
+        G16_TRY(upload_vec(M[m]->wire, &c->d_wid[m], st));
+    }
+    static_assert(sizeof(HFr) == sizeof(Fr), "host and device Fr must share a layout");
+    c->unit_ids = circ.coeffs.size() >= 4 && circ.coeffs[0].is_zero() && circ.coeffs[1] == HFr::one() &&
+                  circ.coeffs[3] == HFr::one().neg();
+    G16_CUDA(cudaMalloc(&c->d_coeffs, sizeof(Fr) * circ.coeffs.size()));
+    G16_CUDA(cudaMemcpyAsync(c->d_coeffs, circ.coeffs.data(), sizeof(Fr) * circ.coeffs.size(), cudaMemcpyHostToDevice, st));
+    // ---- scratch -------------------------------------------------------------------------------
+    G16_TRY(c->d_wires.ensure(sizeof(Fr) * c->wstride * max_batch));
+    G16_TRY(c->d_abc.ensure(sizeof(Fr) * 3 * c->n * max_batch));
+    G16_TRY(c->d_commit_vals.ensure(sizeof(Fr) * (c->n_committed ? c->n_committed : 1) * max_batch));
+    G16_TRY(c->d_out.ensure(sizeof(ProofPoints) * max_batch));
+    G16_CUDA(cudaMalloc(&c->d_tmp_g1, sizeof(G1Affine) * 4 * max_batch));
+    G16_CUDA(cudaMalloc(&c->d_tmp_g2, sizeof(G2Affine) * max_batch));
+    c->h_pinned_bytes = sizeof(Fr) * c->wstride * max_batch;
+    G16_CUDA(cudaMallocHost(&c->h_pinned, c->h_pinned_bytes));
+    const NttDomain* dom;
+    G16_TRY(ctx->ntt.domain(c->logn, st, &dom));
+    G16_CUDA(cudaStreamSynchronize(st));
+    *out = c.release();
+    return G16_OK;
+}
+
+void g16_circuit_free(g16_circuit* c) { delete c; }
+
+int g16_circuit_info(const g16_circuit* c, uint64_t what[16]) {
+    if (!c || !what) return G16_E_ARG;
+    memset(what, 0, 16 * sizeof(uint64_t));
+    what[0] = c->circ.nb_constraints;
+    what[1] = c->nw;
+    what[2] = c->circ.nb_public;
+    what[3] = c->circ.nb_secret;
+    what[4] = c->n;
+    what[5] = c->circ.commitments.size();
+    what[6] = c->nA; what[7] = c->nB; what[8] = c->nK; what[9] = c->nZ; what[10] = c->n_committed;
+    what[11] = c->max_batch;
+    what[12] = c->bA.cfg.c; what[13] = c->bB1.cfg.c; what[14] = c->bKZ.cfg.c; what[15] = c->bB2.cfg.c;
+    return G16_OK;
+}
+
+int g16_prove_wires_dev(g16_circuit* c, size_t n, const void* d_wires, void* d_proof_points) {
+    if (!c || !d_wires || !d_proof_points || n == 0 || n > c->max_batch) {
+        set_error("g16_prove_wires_dev: bad arguments (n must be 1..max_batch)");
+        return G16_E_ARG;
+    }
+    G16_CUDA(cudaSetDevice(c->ctx->device));
+    cudaStream_t st = c->ctx->stream;
+    // wires arrive without the X_* slots: lay them out with stride wstride and r = s = 0
+    G16_CUDA(cudaMemsetAsync(c->d_wires.ptr, 0, sizeof(Fr) * c->wstride * n, st));
+    G16_CUDA(cudaMemcpy2DAsync(c->d_wires.ptr, sizeof(Fr) * c->wstride, d_wires, sizeof(Fr) * c->nw,
+                               sizeof(Fr) * c->nw, n, cudaMemcpyDeviceToDevice, st));
+    k_set_one<<<cdiv(n, 128), 128, 0, st>>>((Fr*)c->d_wires.ptr, c->wstride, c->nw + X_ONE, (uint32_t)n);
+    G16_TRY(prove_device(c, n));
+    G16_CUDA(cudaMemcpyAsync(d_proof_points, c->d_out.ptr, sizeof(ProofPoints) * n, cudaMemcpyDeviceToDevice, st));
+    return G16_OK;
+}
+
+// Shared host path: `wires` holds n full wire vectors (Montgomery) with stride wstride and the X_*
+// slots filled; `commitments` (may be null) the commitment points in canonical form.
+static int prove_from_host_wires(g16_circuit* c, size_t n, const HFr* wires, const G1Affine* commitments,
+                                 uint8_t* proofs) {
+    cudaStream_t st = c->ctx->stream;
+    size_t bytes = sizeof(Fr) * c->wstride * n;
+    memcpy(c->h_pinned, wires, bytes);
+    G16_CUDA(cudaMemcpyAsync(c->d_wires.ptr, c->h_pinned, bytes, cudaMemcpyHostToDevice, st));
+    G16_TRY(prove_device(c, n));
+    std::vector<ProofPoints> pts(n);
+    G16_CUDA(cudaMemcpyAsync(pts.data(), c->d_out.ptr, sizeof(ProofPoints) * n, cudaMemcpyDeviceToHost, st));
+    G16_CUDA(cudaStreamSynchronize(st));
+    const size_t plen = c->has_commitment ? 388 : 324;
+    for (size_t b = 0; b < n; b++)
+        write_proof_bytes(pts[b], commitments ? &commitments[b] : nullptr, proofs + plen * b);
+    return G16_OK;
+}
+
+int g16_prove_wires(g16_circuit* c, size_t n, const uint8_t* wires_be, const uint8_t* rnd, uint8_t* proofs) {
+    if (!c || !wires_be || !proofs || n == 0) {
+        set_error("g16_prove_wires: bad arguments");
+        return G16_E_ARG;
+    }
+    G16_CUDA(cudaSetDevice(c->ctx->device));
+    const size_t plen = c->has_commitment ? 388 : 324;
+    for (size_t done = 0; done < n;) {
+        size_t B = std::min(c->max_batch, n - done);
+        std::vector<HFr> w(c->wstride * B);
+        std::vector<G1Affine> commits(B, G1Affine::inf());
+        std::vector<int> rcs(B, G16_OK);
+        parallel_for(B, [&](size_t b) {
+            const uint8_t* src = wires_be + (done + b) * c->nw * 32;
+            HFr* dst = w.data() + b * c->wstride;
+            for (size_t i = 0; i < c->nw; i++) dst[i] = HFr::from_be(src + 32 * i);
+            HFr r = HFr::zero(), s = HFr::zero();
+            if (rnd) {
+                r = HFr::from_be(rnd + 96 * (done + b));
+                s = HFr::from_be(rnd + 96 * (done + b) + 32);
+            }
+            fill_extras(dst, c->nw, r, s);
+        });
+        if (c->has_commitment) {
+            // commitment point = MSM of the committed wire values over the commitment basis
+            std::vector<HFr> cv(c->n_committed * B);
+            for (size_t b = 0; b < B; b++)
+                for (size_t k = 0; k < c->n_committed; k++) cv[b * c->n_committed + k] = w[b * c->wstride + c->committed_wires[k]];
+            cudaStream_t st = c->ctx->stream;
+            G16_CUDA(cudaMemcpyAsync(c->d_commit_vals.ptr, cv.data(), sizeof(Fr) * cv.size(), cudaMemcpyHostToDevice, st));
+            G16_TRY(c->ctx->g1.run(c->bCommit, (const Fr*)c->d_commit_vals.ptr, c->n_committed, nullptr, 1, B, c->d_tmp_g1, st));
+            size_t nfp = B * 2;
+            k_fp_from_mont<<<cdiv(nfp, 256), 256, 0, st>>>((Fp*)c->d_tmp_g1, nfp);
+            G16_CUDA(cudaMemcpyAsync(commits.data(), c->d_tmp_g1, sizeof(G1Affine) * B, cudaMemcpyDeviceToHost, st));
+            G16_CUDA(cudaStreamSynchronize(st));
+        }
+        G16_TRY(prove_from_host_wires(c, B, w.data(), c->has_commitment ? commits.data() : nullptr, proofs + plen * done));
+        done += B;
+    }
+    return G16_OK;
+}
+
+int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, size_t n_values, const uint8_t* rnd,
+                    uint8_t* proofs, uint8_t* pws, size_t pw_stride) {
+    if (!c || !assignments_be || !proofs || n == 0) {
+        set_error("g16_prove_batch: bad arguments");
+        return G16_E_ARG;
+    }
+    const Circuit& circ = c->circ;
+    const size_t nin = circ.nb_public - 1 + circ.nb_secret;
+    const size_t npub = circ.nb_public - 1;
+    if (n_values != nin) {
+        set_error("g16_prove_batch: assignment has " + std::to_string(n_values) + " values, circuit wants " + std::to_string(nin));
+        return G16_E_ARG;
+    }
+    if (pws && pw_stride < 12 + 32 * npub) {
+        set_error("g16_prove_batch: pw_stride too small");
+        return G16_E_ARG;
+    }
+    G16_CUDA(cudaSetDevice(c->ctx->device));
+    cudaStream_t st = c->ctx->stream;
+    const size_t plen = c->has_commitment ? 388 : 324;
+    for (size_t done = 0; done < n;) {
+        size_t B = std::min(c->max_batch, n - done);
+        std::vector<SolveState> states(B);
+        std::vector<HFr> rs(3 * B);
+        std::vector<int> rcs(B, G16_OK);
+        for (size_t b = 0; b < B; b++)
+            for (int k = 0; k < 3; k++) {
+                if (rnd) rs[3 * b + k] = HFr::from_be(rnd + 96 * (done + b) + 32 * k);
+                else G16_TRY(random_fr(&rs[3 * b + k]));
+            }
+        // ---- phase 1: up to the commitment hint
+        parallel_for(B, [&](size_t b) {
+            std::vector<HFr> asg(nin);
+            const uint8_t* src = assignments_be + (done + b) * nin * 32;
+            for (size_t i = 0; i < nin; i++) asg[i] = HFr::from_be(src + 32 * i);
+            solve_begin(circ, asg.data(), &states[b]);
+            rcs[b] = solve_run(circ, &states[b], &rs[3 * b + 2]);
+        });
+        std::vector<G1Affine> commits(B, G1Affine::inf());
+        bool any_commit = false;
+        for (size_t b = 0; b < B; b++) {
+            if (rcs[b] == SOLVE_NEED_COMMITMENT) any_commit = true;
+            else if (rcs[b] != SOLVE_DONE) {
+                set_error("proof " + std::to_string(done + b) + ": " + states[b].error);
+                return rcs[b];
+            }
+        }
+        if (any_commit) {
+            std::vector<HFr> cv(c->n_committed * B, HFr::zero());
+            for (size_t b = 0; b < B; b++) {
+                if (rcs[b] != SOLVE_NEED_COMMITMENT || states[b].committed.size() != c->n_committed) {
+                    set_error("proof " + std::to_string(done + b) + ": inconsistent commitment hint");
+                    return G16_E_INTERNAL;
+                }
+                memcpy(&cv[b * c->n_committed], states[b].committed.data(), sizeof(HFr) * c->n_committed);
+            }
+            G16_CUDA(cudaMemcpyAsync(c->d_commit_vals.ptr, cv.data(), sizeof(Fr) * cv.size(), cudaMemcpyHostToDevice, st));
+            G16_TRY(c->ctx->g1.run(c->bCommit, (const Fr*)c->d_commit_vals.ptr, c->n_committed, nullptr, 1, B, c->d_tmp_g1, st));
+            size_t nfp = B * 2;
+            k_fp_from_mont<<<cdiv(nfp, 256), 256, 0, st>>>((Fp*)c->d_tmp_g1, nfp);
+            G16_CUDA(cudaMemcpyAsync(commits.data(), c->d_tmp_g1, sizeof(G1Affine) * B, cudaMemcpyDeviceToHost, st));
+            G16_CUDA(cudaStreamSynchronize(st));
+            // ---- challenge + phase 2
+            parallel_for(B, [&](size_t b) {
+                std::vector<uint8_t> msg(64 + 32 * states[b].hashed.size());
+                g1_to_be(commits[b], msg.data());
+                for (size_t k = 0; k < states[b].hashed.size(); k++) states[b].hashed[k].to_be(msg.data() + 64 + 32 * k);
+                solve_provide_challenge(&states[b], hash_to_fr(msg.data(), msg.size(), "bsb22-commitment"));
+                rcs[b] = solve_run(circ, &states[b], &rs[3 * b + 2]);
+            });
+            for (size_t b = 0; b < B; b++)
+                if (rcs[b] != SOLVE_DONE) {
+                    set_error("proof " + std::to_string(done + b) + ": " +
+                              (rcs[b] == SOLVE_NEED_COMMITMENT ? std::string("more than one commitment") : states[b].error));
+                    return rcs[b] == SOLVE_NEED_COMMITMENT ? G16_E_HINT : rcs[b];
+                }
+        }
+        std::vector<HFr> w(c->wstride * B);
+        for (size_t b = 0; b < B; b++) {
+            memcpy(&w[b * c->wstride], states[b].w.data(), sizeof(HFr) * c->nw);
+            fill_extras(&w[b * c->wstride], c->nw, rs[3 * b], rs[3 * b + 1]);
+        }
+        G16_TRY(prove_from_host_wires(c, B, w.data(), c->has_commitment ? commits.data() : nullptr, proofs + plen * done));
+        if (pws) {
+            for (size_t b = 0; b < B; b++) {
+                uint8_t* o = pws + pw_stride * (done + b);
+                uint32_t hdr[3] = {(uint32_t)npub, 0, (uint32_t)npub};
+                for (int k = 0; k < 3; k++) {
+                    o[4 * k] = hdr[k] >> 24; o[4 * k + 1] = hdr[k] >> 16; o[4 * k + 2] = hdr[k] >> 8; o[4 * k + 3] = hdr[k];
+                }
+                for (size_t i = 0; i < npub; i++) states[b].w[1 + i].to_be(o + 12 + 32 * i);
+            }
+        }
+        done += B;
+    }
+    return G16_OK;
+}
+
+int g16_prove(g16_circuit* c, const uint8_t* witness_gz, size_t witness_len, const uint8_t rnd[96], uint8_t* proof,
+              size_t* proof_len, uint8_t* pw, size_t* pw_len) {
+    if (!c || !witness_gz) {
+        set_error("g16_prove: bad arguments");
+        return G16_E_ARG;
+    }
+    std::vector<uint8_t> asg;
+    G16_TRY(witness_to_assignment(c->circ, witness_gz, witness_len, &asg));
+    return g16_prove_assignment(c, asg.data(), asg.size() / 32, rnd, proof, proof_len, pw, pw_len);
+}
+
+int g16_prove_assignment(g16_circuit* c, const uint8_t* assignment_be, size_t n_values, const uint8_t rnd[96],
+                         uint8_t* proof, size_t* proof_len, uint8_t* pw, size_t* pw_len) {
+    if (!c || !proof || !proof_len) {
+        set_error("g16_prove_assignment: bad arguments");
+        return G16_E_ARG;
+    }
+    const size_t plen = c->has_commitment ? 388 : 324;
+    const size_t wlen = 12 + 32 * (c->circ.nb_public - 1);
+    if (*proof_len < plen || (pw && (!pw_len || *pw_len < wlen))) {
+        set_error("g16_prove_assignment: output buffer too small");
+        return G16_E_ARG;
+    }
+    G16_TRY(g16_prove_batch(c, 1, assignment_be, n_values, rnd, proof, pw, wlen));
+    *proof_len = plen;
+    if (pw_len) *pw_len = wlen;
+    return G16_OK;
+}
+
+// Solver-only entry point (no GPU): extends an assignment to the full wire vector.  The BSB22
+// challenges (one per commitment) are supplied by the caller; `committed_be` (optional) receives
+// the committed values the challenge must be derived from.
+int g16_solve_assignment(const uint8_t* ccs, size_t ccs_len, const uint8_t* assignment_be, size_t n_values,
+                         const uint8_t* blinder_be, const uint8_t* challenges_be, size_t n_challenges,
+                         uint8_t* wires_be, size_t wires_cap, uint8_t* committed_be, size_t committed_cap) {
+    if (!ccs || !assignment_be || !wires_be) {
+        set_error("g16_solve_assignment: bad arguments");
+        return G16_E_ARG;
+    }
+    Circuit circ;
+    G16_TRY(parse_ccs(ccs, ccs_len, &circ));
+    const size_t nin = circ.nb_public - 1 + circ.nb_secret;
+    if (n_values != nin || wires_cap < (size_t)circ.nb_wires() * 32) {
+        set_error("g16_solve_assignment: size mismatch (assignment " + std::to_string(n_values) + " vs " + std::to_string(nin) + ")");
+        return G16_E_ARG;
+    }
+    std::vector<HFr> asg(nin);
+    for (size_t i = 0; i < nin; i++) asg[i] = HFr::from_be(assignment_be + 32 * i);
+    HFr blinder = blinder_be ? HFr::from_be(blinder_be) : HFr::zero();
+    SolveState stt;
+    solve_begin(circ, asg.data(), &stt);
+    size_t used = 0;
+    for (;;) {
+        int rc = solve_run(circ, &stt, blinder_be ? &blinder : nullptr);
+        if (rc == SOLVE_DONE) break;
+        if (rc == SOLVE_NEED_COMMITMENT) {
+            if (committed_be && used == 0) {
+                if (committed_cap < stt.committed.size() * 32) {
+                    set_error("g16_solve_assignment: committed buffer too small");
+                    return G16_E_ARG;
+                }
+                for (size_t k = 0; k < stt.committed.size(); k++) stt.committed[k].to_be(committed_be + 32 * k);
+            }
+            if (used >= n_challenges || !challenges_be) {
+                set_error("g16_solve_assignment: circuit needs a commitment challenge that was not supplied");
+                return G16_E_HINT;
+            }
+            solve_provide_challenge(&stt, HFr::from_be(challenges_be + 32 * used));
+            used++;
+            continue;
+        }
+        set_error(stt.error);
+        return rc;
+    }
+    for (size_t i = 0; i < stt.w.size(); i++) stt.w[i].to_be(wires_be + 32 * i);
+    return G16_OK;
+}
+
+}  // extern "C"

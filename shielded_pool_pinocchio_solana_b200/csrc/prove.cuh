@@ -1,0 +1,74 @@
+// prove.cuh -- device-resident circuit handle and the batched Groth16 proving pipeline.
+//
+// Replaces gnark `groth16.Prove` (backend/groth16/bn254/prove.go) as reached through
+// `sunspot prove` (/root/reference/client/proof.helper.ts:64) -- SURVEY.md 3.2.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "capi.cuh"
+#include "ccs.hpp"
+#include "solver.hpp"
+
+namespace g16 {
+
+// host copy of a parsed gnark ProvingKey (points in canonical little-endian limb form)
+struct ProvingKeyHost {
+    uint64_t domain = 0;
+    G1Affine alpha1, beta1, delta1;
+    G2Affine beta2, delta2;
+    std::vector<G1Affine> A, B1, Z, K;
+    std::vector<G2Affine> B2;
+    std::vector<uint8_t> infinity_a, infinity_b;
+    struct CommitKey {
+        std::vector<G1Affine> basis, basis_exp_sigma;
+    };
+    std::vector<CommitKey> commitment_keys;
+};
+
+int parse_pk(const uint8_t* buf, size_t len, ProvingKeyHost* out);
+
+// slots appended to every proof's wire vector on the device
+enum { X_ONE = 0, X_R = 1, X_S = 2, X_NEG_RS = 3, X_COUNT = 8 };
+
+// per-proof results of the device pipeline (canonical little-endian limbs)
+struct ProofPoints {
+    G1Affine ar;
+    G2Affine bs;
+    G1Affine krs;
+    G1Affine pok;
+};
+
+}  // namespace g16
+
+struct g16_circuit {
+    g16_ctx* ctx = nullptr;
+    g16::Circuit circ;
+    unsigned logn = 0;
+    size_t n = 0;           // domain size
+    size_t nw = 0;          // wires
+    size_t wstride = 0;     // nw + X_COUNT
+    size_t max_batch = 0;
+    bool has_commitment = false;
+    int unit_ids = 0;       // coefficient ids 0/1/3 are 0/+1/-1 (gnark's fixed table prefix)
+    size_t n_committed = 0;
+    std::vector<uint32_t> committed_wires;
+    // R1CS on the device: three CSR matrices sharing one coefficient table
+    uint32_t* d_rowptr[3] = {nullptr, nullptr, nullptr};
+    uint32_t* d_cid[3] = {nullptr, nullptr, nullptr};
+    uint32_t* d_wid[3] = {nullptr, nullptr, nullptr};
+    g16::Fr* d_coeffs = nullptr;
+    // MSM bases (window-expanded) and scalar maps
+    g16::MsmBases<g16::Fp> bA, bB1, bKZ, bCommit, bPok;
+    g16::MsmBases<g16::Fp2> bB2;
+    uint32_t *d_mapA = nullptr, *d_mapB = nullptr, *d_mapKZ = nullptr, *d_mapPok = nullptr;
+    size_t nA = 0, nB = 0, nK = 0, nZ = 0;
+    // scratch sized for max_batch proofs
+    g16::DeviceBuf d_wires, d_abc, d_commit_vals, d_out;
+    g16::G1Affine* d_tmp_g1 = nullptr;   // [4][max_batch]: A, B1, KZ, PoK results (Montgomery)
+    g16::G2Affine* d_tmp_g2 = nullptr;   // [max_batch]
+    void* h_pinned = nullptr;            // staging for wires / results
+    size_t h_pinned_bytes = 0;
+    int last_launches = 0;
+    ~g16_circuit();
+};

@@ -1,0 +1,37 @@
+// solver.hpp -- R1CS witness solver (gnark `constraint/bn254/solver.go` semantics): walks the
+// instruction levels of a parsed `.ccs`, solves each R1C row for its single unknown wire and runs
+// the solver hints.  SURVEY.md 3.2 step 1, 8a rows a3 / a3-H.
+//
+// The BSB22 commitment hint needs a Pedersen MSM in the middle of the solve; that MSM runs on the
+// GPU, so the solver is resumable: run() returns SOLVE_NEED_COMMITMENT with the committed values,
+// the caller (prove.cu) computes the commitment for the whole batch in one launch, hashes it and
+// calls provide_challenge() before run() again.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "ccs.hpp"
+
+namespace g16 {
+
+enum { SOLVE_DONE = 0, SOLVE_NEED_COMMITMENT = 100 };
+
+struct SolveState {
+    std::vector<HFr> w;          // all wires, Montgomery
+    std::vector<uint8_t> known;
+    size_t level = 0, pos = 0;   // resume point
+    size_t commitments_done = 0;
+    // filled when run() returns SOLVE_NEED_COMMITMENT
+    std::vector<HFr> committed;  // private committed values, in PrivateCommitted order
+    std::vector<HFr> hashed;     // public/commitment committed values
+    uint32_t challenge_wire = 0;
+    std::string error;           // filled on failure
+};
+
+// assignment: nb_public-1 public values then nb_secret secret values (Montgomery)
+void solve_begin(const Circuit& c, const HFr* assignment, SolveState* st);
+// returns SOLVE_DONE, SOLVE_NEED_COMMITMENT, or a G16_E_* code (st->error holds the message)
+int solve_run(const Circuit& c, SolveState* st, const HFr* blinder);
+void solve_provide_challenge(SolveState* st, const HFr& challenge);
+
+}  // namespace g16
