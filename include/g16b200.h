@@ -58,6 +58,13 @@ int g16_set_stream(g16_ctx* ctx, void* cuda_stream);
 int g16_sync(g16_ctx* ctx);
 /* kernels launched by the last compute call on this context (bench.py `gpu_launches`) */
 int g16_last_launches(g16_ctx* ctx);
+/* Per-kernel device timing with CUDA events on the context stream (bench.py's roofline line).
+ * Slots: 0 = G1 bucket accumulation, 1 = G2 bucket accumulation (ms, launches, points). */
+int g16_profile_enable(g16_ctx* ctx, int enable);
+int g16_profile_read(g16_ctx* ctx, double ms[8], double launches[8], double units[8]);
+/* Convert `count` Fr values (32 B big-endian) to Montgomery limb form in a caller-owned device
+ * buffer (count * 32 bytes), e.g. to stage inputs for the *_dev entry points. */
+int g16_fr_to_device(g16_ctx* ctx, const uint8_t* values_be, size_t count, void* d_out);
 /* Integer-pipe microbenchmark: kind 0 = IMAD (mad.lo.u32), 1 = IMAD.WIDE.U32 with carry
  * (mad.lo.cc/madc.hi.cc pairs, the instruction the field multiplier is made of).
  * Writes instructions per second over the whole chip. */
@@ -115,12 +122,24 @@ void g16_circuit_free(g16_circuit* c);
  *        [12..15] = window bits chosen for the A, B1, K+Z and B2 MSMs */
 int g16_circuit_info(const g16_circuit* c, uint64_t what[16]);
 
+/* Trusted setup on the GPU -- the `sunspot setup` step (noir_circuit/prove_linux.sh:73-79).  The
+ * toxic waste is derived from `seed` (deterministic; use fresh entropy and discard it for a real
+ * ceremony).  Writes gnark raw ProvingKey / VerifyingKey bytes.  Call with pk_out = vk_out = NULL
+ * to obtain the sizes in *pk_len / *vk_len. */
+int g16_setup(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uint8_t* seed, size_t seed_len,
+              uint8_t* pk_out, size_t* pk_len, uint8_t* vk_out, size_t* vk_len);
+
 /* One proof from a Noir witness (`target/<name>.gz`, as written by `nargo execute`).
  * rnd = r || s || commitment blinder (3 x 32 B big-endian); NULL draws them from the OS CSPRNG.
  * proof: G16_PROOF_LEN bytes (gnark Proof.WriteRawTo); pw: 12 + 32*nPublic bytes (witness.WriteTo,
  * public part).  *_len: in = capacity, out = bytes written. */
 int g16_prove(g16_circuit* c, const uint8_t* witness_gz, size_t witness_len, const uint8_t rnd[96],
               uint8_t* proof, size_t* proof_len, uint8_t* pw, size_t* pw_len);
+/* Witness only: full wire vectors (n * nbWires * 32 B big-endian) for n assignments -- the R1CS
+ * solve of gnark's Prove, with the BSB22 commitment MSM on the GPU.  rnd as in g16_prove_batch
+ * (only the blinder is used). */
+int g16_witness_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, size_t n_values, const uint8_t* rnd,
+                      uint8_t* wires_be);
 /* Same, from the public+secret assignment directly (32 B big-endian each, `.ccs` order:
  * Public[1..] then Secret[..]) -- skips the Noir container, runs the R1CS solver. */
 int g16_prove_assignment(g16_circuit* c, const uint8_t* assignment_be, size_t n_values, const uint8_t rnd[96],

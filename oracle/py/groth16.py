@@ -332,6 +332,47 @@ def write_pk(pk):
     return out
 
 
+def read_pk(buf, c):
+    """Inverse of write_pk (needs the Ccs for the wire bookkeeping gnark recomputes at prove time)."""
+    off = 0
+    def u32():
+        nonlocal off
+        v = struct.unpack_from(">I", buf, off)[0]; off += 4; return v
+    def u64():
+        nonlocal off
+        v = struct.unpack_from(">Q", buf, off)[0]; off += 8; return v
+    def g1():
+        nonlocal off
+        p = S.g1_from_bytes(buf[off:off + 64]); off += 64; return p
+    def g2():
+        nonlocal off
+        p = S.g2_from_bytes(buf[off:off + 128]); off += 128; return p
+    pk = {"domain": u64()}
+    off += 5 * 32 + 1
+    pk["alpha1"], pk["beta1"], pk["delta1"] = g1(), g1(), g1()
+    pk["A"] = [g1() for _ in range(u32())]
+    pk["B1"] = [g1() for _ in range(u32())]
+    pk["Z"] = [g1() for _ in range(u32())]
+    pk["K"] = [g1() for _ in range(u32())]
+    pk["beta2"], pk["delta2"] = g2(), g2()
+    pk["B2"] = [g2() for _ in range(u32())]
+    nw, _, _ = u64(), u64(), u64()
+    pk["nb_wires"] = nw
+    n = u32(); pk["infinity_a"] = [bool(x) for x in buf[off:off + n]]; off += n
+    n = u32(); pk["infinity_b"] = [bool(x) for x in buf[off:off + n]]; off += n
+    keys = []
+    for _ in range(u32()):
+        basis = [g1() for _ in range(u32())]
+        keys.append({"basis": basis, "basis_exp_sigma": [g1() for _ in range(u32())]})
+    pk["commitment_keys"] = keys
+    assert off == len(buf)
+    skip = set()
+    for info in c.commitments:
+        skip.add(info["CommitmentIndex"]); skip.update(info["PrivateCommitted"])
+    pk["k_wires"] = [i for i in range(c.nb_public, nw) if i not in skip]
+    return pk
+
+
 def write_vk(vk):
     """VerifyingKey.WriteRawTo -- layout verified on the reference's committed .vk files."""
     out = (S.g1_to_bytes(vk["alpha1"]) + S.g1_to_bytes(vk["beta1"]) + S.g2_to_bytes(vk["beta2"]) +
@@ -448,8 +489,11 @@ def prove(c, pk, assignment, r, s, blinder=None):
 # ------------------------------------------------------------------------------------------
 def verify(vk, proof_bytes, pw_bytes):
     import pairing as Pg
-    proof = read_proof(proof_bytes)
-    pub = read_public_witness(pw_bytes)
+    try:
+        proof = read_proof(proof_bytes)
+        pub = read_public_witness(pw_bytes)
+    except (AssertionError, ValueError, IndexError, struct.error):
+        return False                      # undecodable encoding == rejected, as gnark's ReadFrom would
     ncom = len(vk["commitment_keys"])
     if len(proof["commitments"]) != ncom or len(vk["K"]) != 1 + len(pub) + ncom:
         return False

@@ -45,6 +45,15 @@ PROTOTYPES = {
                                    ctypes.c_size_t, ctypes.c_void_p]),
     "g16_circuit_load": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p,
                                         ctypes.c_size_t, ctypes.c_char_p, c_void_pp]),
+    "g16_setup": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
+                                 ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p,
+                                 ctypes.POINTER(ctypes.c_size_t)]),
+    "g16_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "g16_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
+                                        ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "g16_fr_to_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "g16_witness_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
+                                         ctypes.c_char_p, ctypes.c_char_p]),
     "g16_circuit_free": (None, [ctypes.c_void_p]),
     "g16_circuit_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]),
     "g16_prove": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_char_p,

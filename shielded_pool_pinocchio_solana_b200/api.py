@@ -44,6 +44,18 @@ class Context:
         check(self.lib.g16_measure_imad_peak(self.handle, kind, ctypes.byref(out)))
         return out.value
 
+    def profile_enable(self, on=True):
+        check(self.lib.g16_profile_enable(self.handle, int(on)))
+
+    def profile_read(self):
+        """-> {slot: (ms, launches, units)}; slot 0 = G1 bucket accumulation, 1 = G2."""
+        ms, ln, un = ((ctypes.c_double * 8)() for _ in range(3))
+        check(self.lib.g16_profile_read(self.handle, ms, ln, un))
+        return {i: (ms[i], ln[i], un[i]) for i in range(8)}
+
+    def fr_to_device(self, values_be: bytes, d_ptr):
+        check(self.lib.g16_fr_to_device(self.handle, values_be, len(values_be) // 32, ctypes.c_void_p(d_ptr)))
+
     def generate_points(self, n, seed=0xB200, group="g1") -> bytes:
         """Synthetic bases P_i = [k_i]G computed on the device (gnark raw bytes)."""
         size = 64 if group == "g1" else 128
@@ -70,6 +82,19 @@ class Context:
 
     def compute_h_dev(self, d_abc_ptr, logn, nproofs=1):
         check(self.lib.g16_compute_h_dev(self.handle, ctypes.c_void_p(d_abc_ptr), logn, nproofs))
+
+    def setup(self, ccs: bytes, seed: bytes):
+        """`sunspot setup` on the GPU: -> (pk bytes, vk bytes) in gnark raw format."""
+        pl, vl = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        check(self.lib.g16_setup(self.handle, ccs, len(ccs), seed, len(seed), None, ctypes.byref(pl), None,
+                                 ctypes.byref(vl)))
+        pk, vk = ctypes.create_string_buffer(pl.value), ctypes.create_string_buffer(vl.value)
+        check(self.lib.g16_setup(self.handle, ccs, len(ccs), seed, len(seed), pk, ctypes.byref(pl), vk,
+                                 ctypes.byref(vl)))
+        return pk.raw, vk.raw
+
+    def load_circuit(self, ccs: bytes, pk: bytes):
+        return Circuit(self, ccs, pk)
 
     def load_bases(self, points_be: bytes, group="g1", window=0, batch_hint=1):
         return Bases(self, points_be, group, window, batch_hint)
@@ -162,6 +187,12 @@ class Circuit:
         proofs = ctypes.create_string_buffer(n * self.proof_len)
         check(self.ctx.lib.g16_prove_wires(self.handle, n, wires_be, rnd, proofs))
         return [proofs.raw[i * self.proof_len:(i + 1) * self.proof_len] for i in range(n)]
+
+    def witness_batch(self, assignments_be: bytes, n, rnd: bytes = None) -> bytes:
+        """Full wire vectors (n * nb_wires * 32 B BE): the R1CS solve only."""
+        out = ctypes.create_string_buffer(n * self.info["nb_wires"] * 32)
+        check(self.ctx.lib.g16_witness_batch(self.handle, n, assignments_be, self.n_values, rnd, out))
+        return out.raw
 
     def prove_wires_dev(self, d_wires_ptr, n, d_out_ptr):
         check(self.ctx.lib.g16_prove_wires_dev(self.handle, n, ctypes.c_void_p(d_wires_ptr), ctypes.c_void_p(d_out_ptr)))

@@ -71,6 +71,11 @@ DeviceBuf::~DeviceBuf() {
     if (ptr) cudaFree(ptr);
 }
 
+static __global__ void k_fr_to_mont_pub(Fr* v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = v[i].to_mont();
+}
+
 // ---- integer-pipe microbenchmark ---------------------------------------------------------------
 // 8 independent dependency chains per thread, 2048 resident threads per SM: measures the issue
 // rate of the instruction, not its latency.
@@ -140,6 +145,8 @@ int g16_init(const int* device_ids, int n_devices, g16_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     G16_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    c->g1.prof = &c->prof;
+    c->g2.prof = &c->prof;
     *out = c;
     return G16_OK;
 }
@@ -169,6 +176,29 @@ int g16_sync(g16_ctx* ctx) {
 }
 
 int g16_last_launches(g16_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+int g16_profile_enable(g16_ctx* ctx, int enable) {
+    if (!ctx) return G16_E_ARG;
+    ctx->prof.enabled = enable != 0;
+    return G16_OK;
+}
+int g16_profile_read(g16_ctx* ctx, double ms[8], double launches[8], double units[8]) {
+    if (!ctx || !ms || !launches || !units) return G16_E_ARG;
+    G16_CUDA(cudaSetDevice(ctx->device));
+    ctx->prof.read(ms, launches, units);
+    return G16_OK;
+}
+
+int g16_fr_to_device(g16_ctx* ctx, const uint8_t* values_be, size_t count, void* d_out) {
+    if (!ctx || !values_be || !d_out) return G16_E_ARG;
+    G16_CUDA(cudaSetDevice(ctx->device));
+    std::vector<Fr> tmp(count);
+    for (size_t i = 0; i < count; i++) be32_to_limbs(values_be + 32 * i, tmp[i].v);
+    G16_CUDA(cudaMemcpyAsync(d_out, tmp.data(), sizeof(Fr) * count, cudaMemcpyHostToDevice, ctx->stream));
+    k_fr_to_mont_pub<<<cdiv(count, 256), 256, 0, ctx->stream>>>((Fr*)d_out, count);
+    G16_CUDA(cudaStreamSynchronize(ctx->stream));
+    return G16_OK;
+}
 
 int g16_measure_imad_peak(g16_ctx* ctx, int kind, double* instr_per_s) {
     if (!ctx || !instr_per_s) return G16_E_ARG;

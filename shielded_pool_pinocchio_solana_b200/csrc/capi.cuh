@@ -32,6 +32,7 @@ struct g16_ctx {
     g16::MsmRunner<g16::Fp> g1;
     g16::MsmRunner<g16::Fp2> g2;
     g16::NttEngine ntt;
+    g16::KernelProfiler prof;
     g16::DeviceBuf scratch, scalars, results;
 };
 

@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/g16b200.h"
 
@@ -32,6 +33,57 @@ const char* get_error();
         int _rc = (expr);              \
         if (_rc != ::G16_OK) return _rc; \
     } while (0)
+
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline line).
+// Events are pooled and only read back in read(): nothing synchronises inside the timed region.
+struct KernelProfiler {
+    struct Rec {
+        cudaEvent_t a, b;
+        int tag;
+        double units;
+    };
+    bool enabled = false;
+    std::vector<Rec> recs;
+    size_t used = 0;
+    void begin(int tag, double units, cudaStream_t st) {
+        if (!enabled) return;
+        if (used == recs.size()) {
+            Rec r;
+            cudaEventCreate(&r.a);
+            cudaEventCreate(&r.b);
+            recs.push_back(r);
+        }
+        recs[used].tag = tag;
+        recs[used].units = units;
+        cudaEventRecord(recs[used].a, st);
+    }
+    void end(cudaStream_t st) {
+        if (!enabled) return;
+        cudaEventRecord(recs[used].b, st);
+        used++;
+    }
+    // sums per tag (0..7): milliseconds, launches, units
+    void read(double ms[8], double launches[8], double units[8]) {
+        for (int i = 0; i < 8; i++) ms[i] = launches[i] = units[i] = 0;
+        for (size_t i = 0; i < used; i++) {
+            cudaEventSynchronize(recs[i].b);
+            float t = 0;
+            cudaEventElapsedTime(&t, recs[i].a, recs[i].b);
+            int g = recs[i].tag & 7;
+            ms[g] += t;
+            launches[g] += 1;
+            units[g] += recs[i].units;
+        }
+        used = 0;
+    }
+    ~KernelProfiler() {
+        for (auto& r : recs) {
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+    }
+};
+enum { PROF_MSM_ACC_G1 = 0, PROF_MSM_ACC_G2 = 1, PROF_NTT = 2, PROF_MSM_OTHER = 3, PROF_SPMV = 4 };
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 

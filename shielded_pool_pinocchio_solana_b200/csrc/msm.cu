@@ -133,8 +133,10 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     k_msm_digits<1><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery, cfg,
                                                          counts, entries);
     // after the scatter, counts[k] (the cursor) is the END of bucket k
+    if (prof) prof->begin(sizeof(F) == sizeof(Fp) ? PROF_MSM_ACC_G1 : PROF_MSM_ACC_G2, (double)batch * n, st);
     k_msm_accumulate<F><<<cdiv(nbuckets, 128), 128, 0, st>>>(bases.table, entries, starts, counts, buckets,
                                                              (uint32_t)nbuckets);
+    if (prof) prof->end(st);
     const uint32_t nseg = cfg.nb / cfg.seg;
     const size_t nseg_total = batch * nseg;
     k_msm_reduce1<F><<<cdiv(nseg_total, 128), 128, 0, st>>>(buckets, cfg.nb, cfg.seg, (uint32_t)nseg_total, seg_acc,

@@ -373,6 +373,7 @@ class MsmRunner {
     void release();
     // kernels launched by the last run() (for bench.py's gpu_launches)
     int launches = 0;
+    KernelProfiler* prof = nullptr;   // optional: times the accumulate kernel
 
    private:
     int reserve(const MsmBases<F>& bases, size_t batch);

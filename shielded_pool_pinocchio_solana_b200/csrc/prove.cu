@@ -685,6 +685,81 @@ int g16_prove(g16_circuit* c, const uint8_t* witness_gz, size_t witness_len, con
     return g16_prove_assignment(c, asg.data(), asg.size() / 32, rnd, proof, proof_len, pw, pw_len);
 }
 
+// Full wire vectors only (two-phase solve with the commitment MSM on the GPU), no proof.
+int g16_witness_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, size_t n_values, const uint8_t* rnd,
+                      uint8_t* wires_be) {
+    if (!c || !assignments_be || !wires_be || n == 0) {
+        set_error("g16_witness_batch: bad arguments");
+        return G16_E_ARG;
+    }
+    const Circuit& circ = c->circ;
+    const size_t nin = circ.nb_public - 1 + circ.nb_secret;
+    if (n_values != nin) {
+        set_error("g16_witness_batch: assignment size mismatch");
+        return G16_E_ARG;
+    }
+    G16_CUDA(cudaSetDevice(c->ctx->device));
+    cudaStream_t st = c->ctx->stream;
+    for (size_t done = 0; done < n;) {
+        size_t B = std::min(c->max_batch, n - done);
+        std::vector<SolveState> states(B);
+        std::vector<HFr> bl(B);
+        std::vector<int> rcs(B, G16_OK);
+        for (size_t b = 0; b < B; b++) {
+            if (rnd) bl[b] = HFr::from_be(rnd + 96 * (done + b) + 64);
+            else G16_TRY(random_fr(&bl[b]));
+        }
+        parallel_for(B, [&](size_t b) {
+            std::vector<HFr> asg(nin);
+            const uint8_t* src = assignments_be + (done + b) * nin * 32;
+            for (size_t i = 0; i < nin; i++) asg[i] = HFr::from_be(src + 32 * i);
+            solve_begin(circ, asg.data(), &states[b]);
+            rcs[b] = solve_run(circ, &states[b], &bl[b]);
+        });
+        bool any_commit = false;
+        for (size_t b = 0; b < B; b++) {
+            if (rcs[b] == SOLVE_NEED_COMMITMENT) any_commit = true;
+            else if (rcs[b] != SOLVE_DONE) {
+                set_error("witness " + std::to_string(done + b) + ": " + states[b].error);
+                return rcs[b];
+            }
+        }
+        if (any_commit) {
+            std::vector<HFr> cv(c->n_committed * B, HFr::zero());
+            std::vector<G1Affine> commits(B, G1Affine::inf());
+            for (size_t b = 0; b < B; b++) {
+                if (rcs[b] != SOLVE_NEED_COMMITMENT || states[b].committed.size() != c->n_committed) {
+                    set_error("witness " + std::to_string(done + b) + ": inconsistent commitment hint");
+                    return G16_E_INTERNAL;
+                }
+                memcpy(&cv[b * c->n_committed], states[b].committed.data(), sizeof(HFr) * c->n_committed);
+            }
+            G16_CUDA(cudaMemcpyAsync(c->d_commit_vals.ptr, cv.data(), sizeof(Fr) * cv.size(), cudaMemcpyHostToDevice, st));
+            G16_TRY(c->ctx->g1.run(c->bCommit, (const Fr*)c->d_commit_vals.ptr, c->n_committed, nullptr, 1, B, c->d_tmp_g1, st));
+            k_fp_from_mont<<<cdiv(B * 2, 256), 256, 0, st>>>((Fp*)c->d_tmp_g1, B * 2);
+            G16_CUDA(cudaMemcpyAsync(commits.data(), c->d_tmp_g1, sizeof(G1Affine) * B, cudaMemcpyDeviceToHost, st));
+            G16_CUDA(cudaStreamSynchronize(st));
+            parallel_for(B, [&](size_t b) {
+                std::vector<uint8_t> msg(64 + 32 * states[b].hashed.size());
+                g1_to_be(commits[b], msg.data());
+                for (size_t k = 0; k < states[b].hashed.size(); k++) states[b].hashed[k].to_be(msg.data() + 64 + 32 * k);
+                solve_provide_challenge(&states[b], hash_to_fr(msg.data(), msg.size(), "bsb22-commitment"));
+                rcs[b] = solve_run(circ, &states[b], &bl[b]);
+            });
+            for (size_t b = 0; b < B; b++)
+                if (rcs[b] != SOLVE_DONE) {
+                    set_error("witness " + std::to_string(done + b) + ": " + states[b].error);
+                    return rcs[b] == SOLVE_NEED_COMMITMENT ? G16_E_HINT : rcs[b];
+                }
+        }
+        parallel_for(B, [&](size_t b) {
+            for (size_t i = 0; i < c->nw; i++) states[b].w[i].to_be(wires_be + ((done + b) * c->nw + i) * 32);
+        });
+        done += B;
+    }
+    return G16_OK;
+}
+
 int g16_prove_assignment(g16_circuit* c, const uint8_t* assignment_be, size_t n_values, const uint8_t rnd[96],
                          uint8_t* proof, size_t* proof_len, uint8_t* pw, size_t* pw_len) {
     if (!c || !proof || !proof_len) {

@@ -132,7 +132,8 @@ def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=4
     next_wire = first_internal
     wire_level = {w: -1 for w in range(first_internal)}   # inputs are known before level 0
 
-    instr = []      # (blueprint, calldata list, defines [wires], level)
+    instr = []      # (blueprint, calldata list, level)
+    row_count = [0]
     def lvl(wires):
         return 1 + max([wire_level[w] for w in wires if w != CONST_WIRE] + [-1])
 
@@ -147,6 +148,7 @@ def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=4
         if defines is not None:
             wire_level[defines] = level
         instr.append((1, cd, level))
+        row_count[0] += 1
 
     def add_hint(hid, inputs, nout):
         nonlocal next_wire
@@ -192,7 +194,7 @@ def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=4
 
     known = list(range(0, first_internal)) + [iz] + bits + limbs + mult
     n_rows_target = n_constraints
-    rows_so_far = lambda: sum(1 for bp, _, _ in instr if bp == 1)
+    rows_so_far = lambda: row_count[0]
 
     # ---- commitment (Randomize blinder + BSB22 placeholder) -----------------------------------
     commit_info = None
@@ -201,19 +203,19 @@ def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=4
         nonlocal next_wire
         new = next_wire
         next_wire += 1
-        p = rng.choice(known[-4096:]) if rng.random() < 0.5 else rng.choice(known)
+        nk = len(known)
+        pick = lambda: known[rng.randrange(nk)]
+        recent = lambda span: known[rng.randrange(max(0, nk - span), nk)]
+        p = recent(4096) if rng.random() < 0.5 else pick()
         L = [(rng.randrange(5, 5 + n_coeffs), p)]
         if rng.random() < 0.02:
-            L.append((rng.randrange(5, 5 + n_coeffs), rng.choice(known)))
-        Rr = [(rng.randrange(1, 5 + n_coeffs), rng.choice(known[-64:] if rng.random() < 0.3 else known))
-              for _ in range(dens_b)]
+            L.append((rng.randrange(5, 5 + n_coeffs), pick()))
+        Rr = [(rng.randrange(1, 5 + n_coeffs), recent(64) if rng.random() < 0.3 else pick()) for _ in range(dens_b)]
         if rng.random() < 0.06:
             Rr.append((1, 0))
-        O = [(1, new)]
+        O = [(1, new), (rng.randrange(1, 5 + n_coeffs), pick())]
         if rng.random() < frac_c2:
-            O.append((rng.randrange(1, 5 + n_coeffs), rng.choice(known)))
-        if rng.random() < 0.5:
-            O.append((rng.randrange(1, 5 + n_coeffs), rng.choice(known)))
+            O.append((rng.randrange(1, 5 + n_coeffs), pick()))
         add_r1c(L, Rr, O, defines=new)
         known.append(new)
         return new

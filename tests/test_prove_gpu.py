@@ -85,3 +85,31 @@ def test_mismatched_key_is_rejected(ctx, golden):
     other = synth.build(900, n_public=2, n_secret=16, n_committed=12, seed=8)
     with pytest.raises(g16.G16Error):
         g16.Circuit(ctx, other.ccs, bytes.fromhex(golden["pk"]))
+
+
+def test_gpu_setup_matches_oracle_key(ctx, golden):
+    """`sunspot setup` stand-in: the GPU-built pk / vk equal the oracle's byte for byte."""
+    pk, vk = ctx.setup(bytes.fromhex(golden["ccs"]), b"golden-small")
+    assert vk.hex() == golden["vk"]
+    assert pk.hex() == golden["pk"]
+
+
+def test_audit_like_circuit_proves_and_verifies(ctx):
+    """Config 2 stand-in (26,000 constraints, domain 2^15, 2 public inputs, 1 commitment): GPU
+    setup + GPU proofs, checked by the oracle's pairing verifier and byte framing."""
+    import groth16 as G
+    from shielded_pool_pinocchio_solana_b200 import synth
+    sc = synth.audit_like()
+    pk, vk = ctx.setup(sc.ccs, b"audit-like")
+    circ = ctx.load_circuit(sc.ccs, pk)
+    assert circ.info["domain"] == 1 << 15 and circ.info["nb_constraints"] == 26000
+    n = 3
+    asg = b"".join(sc.assignment_bytes(i) for i in range(n))
+    proofs, pws = circ.prove_batch(asg, n)
+    assert all(len(p) == 388 for p in proofs) and all(len(w) == 76 for w in pws)
+    vkd = G.read_vk(vk)
+    assert len(vkd["K"]) == 4          # like audit_circuit/target/rlwe_audit.vk
+    assert G.verify(vkd, proofs[0], pws[0])
+    assert G.verify(vkd, proofs[2], pws[2])
+    assert not G.verify(vkd, proofs[1], pws[0][:-1] + bytes([pws[0][-1] ^ 1]))
+    circ.free()
