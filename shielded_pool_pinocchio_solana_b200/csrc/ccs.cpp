@@ -391,6 +391,21 @@ int parse_ccs(const uint8_t* buf, size_t len, Circuit* out) {
             if (HFr::geq_mod(x.l)) throw ParseError("coefficient not reduced");
         }
         if (r.off != len) throw ParseError("trailing bytes after the coefficient table");
+        {   // batch inversion of the table (Montgomery's trick)
+            c.coeff_invs = c.coeffs;
+            std::vector<HFr> pref(ncoef);
+            HFr acc = HFr::one();
+            for (size_t i = 0; i < ncoef; i++) {
+                pref[i] = acc;
+                if (!c.coeffs[i].is_zero()) acc = acc * c.coeffs[i];
+            }
+            HFr inv = acc.inverse();
+            for (size_t i = ncoef; i-- > 0;) {
+                if (c.coeffs[i].is_zero()) continue;
+                c.coeff_invs[i] = inv * pref[i];
+                inv = inv * c.coeffs[i];
+            }
+        }
         size_t nrows = 0;
         for (auto b : c.blueprint) nrows += (b == 1);
         if (nrows != c.nb_constraints) throw ParseError("NbConstraints does not match the R1C instruction count");

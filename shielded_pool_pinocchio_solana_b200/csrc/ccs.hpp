@@ -42,6 +42,7 @@ struct Circuit {
     std::vector<uint64_t> start_calldata;
     std::vector<uint32_t> calldata;
     std::vector<HFr> coeffs;  // Montgomery
+    std::vector<HFr> coeff_invs;  // 1/coeff (0 for 0), for the solver
     // sizes
     uint32_t nb_public = 0;   // including the ONE wire
     uint32_t nb_secret = 0;

@@ -63,7 +63,8 @@ int MsmBases<F>::load(const Affine<F>* host_pts, size_t n_, int c, int canonical
 
 template <class F>
 void MsmRunner<F>::release() {
-    cudaFree(counts); cudaFree(starts); cudaFree(tile_sums); cudaFree(entries);
+    cudaFree(counts); cudaFree(starts); cudaFree(tile_sums); cudaFree(entries); cudaFree(order); cudaFree(size_hist);
+    order = size_hist = nullptr;
     cudaFree(buckets); cudaFree(seg_acc); cudaFree(seg_run);
     counts = starts = tile_sums = entries = nullptr;
     buckets = seg_acc = seg_run = nullptr;
@@ -81,8 +82,10 @@ int MsmRunner<F>::reserve(const MsmBases<F>& bases, size_t batch) {
         return G16_E_ARG;
     }
     if (nbuckets > cap_buckets) {
-        cudaFree(counts); cudaFree(starts); cudaFree(buckets);
-        counts = starts = nullptr; buckets = nullptr; cap_buckets = 0;
+        cudaFree(counts); cudaFree(starts); cudaFree(buckets); cudaFree(order);
+        counts = starts = order = nullptr; buckets = nullptr; cap_buckets = 0;
+        G16_CUDA(cudaMalloc(&order, 4 * nbuckets));
+        if (!size_hist) G16_CUDA(cudaMalloc(&size_hist, 4 * 2 * MSM_SIZE_BINS));
         G16_CUDA(cudaMalloc(&counts, 4 * nbuckets));
         G16_CUDA(cudaMalloc(&starts, 4 * nbuckets));
         G16_CUDA(cudaMalloc(&buckets, sizeof(XYZZ<F>) * nbuckets));
@@ -133,8 +136,14 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     k_msm_digits<1><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery, cfg,
                                                          counts, entries);
     // after the scatter, counts[k] (the cursor) is the END of bucket k
+    // schedule the buckets by decreasing size
+    G16_CUDA(cudaMemsetAsync(size_hist, 0, 4 * MSM_SIZE_BINS, st));
+    const unsigned ogrid = cdiv(nbuckets, MSM_ORDER_THREADS * MSM_ORDER_ITEMS);
+    k_msm_size_hist<<<ogrid, MSM_ORDER_THREADS, 0, st>>>(starts, counts, (uint32_t)nbuckets, size_hist);
+    k_msm_size_bins<<<1, MSM_SIZE_BINS, 0, st>>>(size_hist, size_hist + MSM_SIZE_BINS);
+    k_msm_order<<<ogrid, MSM_ORDER_THREADS, 0, st>>>(starts, counts, (uint32_t)nbuckets, size_hist + MSM_SIZE_BINS, order);
     if (prof) prof->begin(sizeof(F) == sizeof(Fp) ? PROF_MSM_ACC_G1 : PROF_MSM_ACC_G2, (double)batch * n, st);
-    k_msm_accumulate<F><<<cdiv(nbuckets, 128), 128, 0, st>>>(bases.table, entries, starts, counts, buckets,
+    k_msm_accumulate<F><<<cdiv(nbuckets, 128), 128, 0, st>>>(bases.table, entries, starts, counts, order, buckets,
                                                              (uint32_t)nbuckets);
     if (prof) prof->end(st);
     const uint32_t nseg = cfg.nb / cfg.seg;
@@ -142,7 +151,7 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     k_msm_reduce1<F><<<cdiv(nseg_total, 128), 128, 0, st>>>(buckets, cfg.nb, cfg.seg, (uint32_t)nseg_total, seg_acc,
                                                             seg_run);
     k_msm_reduce2<F><<<(unsigned)batch, MSM_R2_THREADS, 0, st>>>(seg_acc, seg_run, nseg, cfg.seg, d_out);
-    launches = 8;
+    launches = 11;
     G16_CUDA(cudaGetLastError());
     return G16_OK;
 }

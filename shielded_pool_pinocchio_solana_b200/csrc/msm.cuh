@@ -195,15 +195,85 @@ static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32
 }
 
 // ---------------------------------------------------------------------------------------------
+// schedule: buckets in order of decreasing size
+// ---------------------------------------------------------------------------------------------
+// A warp runs as long as its fullest bucket, and bucket sizes are Poisson-distributed (mean
+// n*W/2^(c-1), often only 20-30), so lanes would idle a third of the time.  A counting sort of the
+// bucket ids by size (1024 size classes, descending) gives every warp 32 buckets of (nearly)
+// equal size and starts the heaviest buckets first (longest-processing-time-first).
+constexpr int MSM_SIZE_BINS = 1024;
+constexpr int MSM_ORDER_THREADS = 256;
+constexpr int MSM_ORDER_ITEMS = 8;
+
+static __global__ void __launch_bounds__(MSM_ORDER_THREADS)
+k_msm_size_hist(const uint32_t* __restrict__ starts, const uint32_t* __restrict__ ends, uint32_t nbuckets,
+                uint32_t* __restrict__ hist) {
+    __shared__ uint32_t lh[MSM_SIZE_BINS];
+    for (int i = threadIdx.x; i < MSM_SIZE_BINS; i += MSM_ORDER_THREADS) lh[i] = 0;
+    __syncthreads();
+    uint32_t base = blockIdx.x * MSM_ORDER_THREADS * MSM_ORDER_ITEMS;
+#pragma unroll
+    for (int it = 0; it < MSM_ORDER_ITEMS; it++) {
+        uint32_t k = base + it * MSM_ORDER_THREADS + threadIdx.x;
+        if (k < nbuckets) atomicAdd(&lh[min(ends[k] - starts[k], (uint32_t)MSM_SIZE_BINS - 1)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < MSM_SIZE_BINS; i += MSM_ORDER_THREADS)
+        if (lh[i]) atomicAdd(&hist[i], lh[i]);
+}
+// cursor[s] = number of buckets strictly larger than s  (single CTA of MSM_SIZE_BINS threads)
+static __global__ void __launch_bounds__(MSM_SIZE_BINS) k_msm_size_bins(const uint32_t* __restrict__ hist,
+                                                                        uint32_t* __restrict__ cursor) {
+    __shared__ uint32_t sh[MSM_SIZE_BINS];
+    int t = threadIdx.x;
+    sh[t] = hist[MSM_SIZE_BINS - 1 - t];  // descending size
+    __syncthreads();
+    for (int o = 1; o < MSM_SIZE_BINS; o <<= 1) {
+        uint32_t v = t >= o ? sh[t - o] : 0;
+        __syncthreads();
+        sh[t] += v;
+        __syncthreads();
+    }
+    cursor[MSM_SIZE_BINS - 1 - t] = sh[t] - hist[MSM_SIZE_BINS - 1 - t];
+}
+static __global__ void __launch_bounds__(MSM_ORDER_THREADS)
+k_msm_order(const uint32_t* __restrict__ starts, const uint32_t* __restrict__ ends, uint32_t nbuckets,
+            uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
+    __shared__ uint32_t lh[MSM_SIZE_BINS], lbase[MSM_SIZE_BINS];
+    for (int i = threadIdx.x; i < MSM_SIZE_BINS; i += MSM_ORDER_THREADS) lh[i] = 0;
+    __syncthreads();
+    uint32_t base = blockIdx.x * MSM_ORDER_THREADS * MSM_ORDER_ITEMS;
+    uint32_t sz[MSM_ORDER_ITEMS], rank[MSM_ORDER_ITEMS];
+#pragma unroll
+    for (int it = 0; it < MSM_ORDER_ITEMS; it++) {
+        uint32_t k = base + it * MSM_ORDER_THREADS + threadIdx.x;
+        if (k < nbuckets) {
+            sz[it] = min(ends[k] - starts[k], (uint32_t)MSM_SIZE_BINS - 1);
+            rank[it] = atomicAdd(&lh[sz[it]], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < MSM_SIZE_BINS; i += MSM_ORDER_THREADS)
+        if (lh[i]) lbase[i] = atomicAdd(&cursor[i], lh[i]);
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < MSM_ORDER_ITEMS; it++) {
+        uint32_t k = base + it * MSM_ORDER_THREADS + threadIdx.x;
+        if (k < nbuckets) order[lbase[sz[it]] + rank[it]] = k;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // bucket accumulation: one thread per (batch, bucket)
 // ---------------------------------------------------------------------------------------------
 template <class F>
 __global__ void __launch_bounds__(128)
 k_msm_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ entries,
                  const uint32_t* __restrict__ starts, const uint32_t* __restrict__ ends,
-                 XYZZ<F>* __restrict__ buckets, uint32_t total_buckets) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= total_buckets) return;
+                 const uint32_t* __restrict__ order, XYZZ<F>* __restrict__ buckets, uint32_t total_buckets) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_buckets) return;
+    uint32_t k = order[t];
     uint32_t s = starts[k], e = ends[k];
     XYZZ<F> acc = XYZZ<F>::inf();
     if (s < e) {
@@ -379,7 +449,7 @@ class MsmRunner {
     int reserve(const MsmBases<F>& bases, size_t batch);
     size_t cap_buckets = 0, cap_entries = 0, cap_segs = 0, cap_tiles = 0;
     uint32_t *counts = nullptr /* doubles as the scatter cursor */, *starts = nullptr, *tile_sums = nullptr,
-             *entries = nullptr;
+             *entries = nullptr, *order = nullptr, *size_hist = nullptr /* [2][MSM_SIZE_BINS]: hist, cursor */;
     XYZZ<F>*buckets = nullptr, *seg_acc = nullptr, *seg_run = nullptr;
 };
 

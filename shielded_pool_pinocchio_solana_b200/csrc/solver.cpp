@@ -16,12 +16,15 @@ struct Lin {
     int unknowns = 0;     // distinct unknown wires seen (0, 1, or >1)
     uint32_t unk_wire = 0;
     HFr unk_coeff;        // accumulated coefficient of that wire
+    uint32_t unk_cid = 0; // coefficient id when the wire appears in exactly one term
+    int unk_terms = 0;
 };
 
 inline void eval_terms(const Circuit& c, const SolveState& st, const uint32_t* terms, uint32_t n, Lin* out) {
     out->sum = HFr::zero();
     out->unknowns = 0;
     out->unk_coeff = HFr::zero();
+    out->unk_terms = 0;
     static const HFr ONE = HFr::one();
     for (uint32_t k = 0; k < n; k++) {
         uint32_t cid = terms[2 * k], wid = terms[2 * k + 1];
@@ -34,6 +37,8 @@ inline void eval_terms(const Circuit& c, const SolveState& st, const uint32_t* t
             if (out->unknowns == 0 || out->unk_wire != wid) out->unknowns++;
             out->unk_wire = wid;
             out->unk_coeff = out->unk_coeff + coef;
+            out->unk_cid = cid;
+            out->unk_terms++;
             continue;
         }
         if (coef == ONE) out->sum = out->sum + st.w[wid];
@@ -168,15 +173,17 @@ int run_r1c(const Circuit& c, SolveState* st, uint32_t instr) {
     if (!same || (L.unknowns && L.unk_wire != wid) || (Rr.unknowns && Rr.unk_wire != wid) || (O.unknowns && O.unk_wire != wid) ||
         unknowns != 1)
         return fail(st, G16_E_UNSAT, "constraint #" + std::to_string(row) + " has more than one unsolved wire");
+    // 1/coefficient: from the table precomputed at parse time unless the wire repeats in the row
+    auto coeff_inv = [&](const Lin& l) { return l.unk_terms == 1 ? c.coeff_invs[l.unk_cid] : l.unk_coeff.inverse(); };
     HFr val;
     if (O.unknowns) {
-        val = (L.sum * Rr.sum - O.sum) * O.unk_coeff.inverse();
+        val = (L.sum * Rr.sum - O.sum) * coeff_inv(O);
     } else if (L.unknowns) {
         if (Rr.sum.is_zero()) return fail(st, G16_E_UNSAT, "constraint #" + std::to_string(row) + ": division by zero");
-        val = (O.sum * Rr.sum.inverse() - L.sum) * L.unk_coeff.inverse();
+        val = (O.sum * Rr.sum.inverse() - L.sum) * coeff_inv(L);
     } else {
         if (L.sum.is_zero()) return fail(st, G16_E_UNSAT, "constraint #" + std::to_string(row) + ": division by zero");
-        val = (O.sum * L.sum.inverse() - Rr.sum) * Rr.unk_coeff.inverse();
+        val = (O.sum * L.sum.inverse() - Rr.sum) * coeff_inv(Rr);
     }
     st->w[wid] = val;
     st->known[wid] = 1;
