@@ -1,0 +1,97 @@
+// cli.cpp -- `g16prove`: command-line stand-in for the sunspot binary on the proving path.
+//
+//   g16prove prove <acir.json> <witness.gz> <ccs> <pk>      same argv as `sunspot prove`
+//        (/root/reference/client/proof.helper.ts:64, noir_circuit/prove_linux.sh:83); writes
+//        <dir-of-ccs>/<name>.proof and <name>.pw, the files proof.helper.ts:68-69 and
+//        client/generate-proof-hex.ts:18-27 read back.
+//   g16prove setup <ccs> <pk-out> <vk-out> [seed]           `sunspot setup` (prove_linux.sh:78)
+// Exit code 0 on success; non-zero with the library's message on stderr otherwise (execSync throws
+// on non-zero exit, which is the reference's only error channel).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <fstream>
+#include <iterator>
+#include <string>
+#include <vector>
+
+#include "../../include/g16b200.h"
+
+static bool slurp(const char* path, std::vector<uint8_t>* out) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    out->assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    return true;
+}
+static bool spill(const std::string& path, const uint8_t* p, size_t n) {
+    std::ofstream f(path, std::ios::binary);
+    f.write((const char*)p, (std::streamsize)n);
+    return (bool)f;
+}
+static int die(const char* what) {
+    fprintf(stderr, "g16prove: %s: %s\n", what, g16_last_error());
+    return 1;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) {
+        fprintf(stderr, "usage: g16prove prove <acir.json> <witness.gz> <ccs> <pk>\n"
+                        "       g16prove setup <ccs> <pk-out> <vk-out> [seed]\n");
+        return 2;
+    }
+    int dev = getenv("G16_DEVICE") ? atoi(getenv("G16_DEVICE")) : 0;
+    g16_ctx* ctx = nullptr;
+    if (g16_init(&dev, 1, &ctx) != G16_OK) return die("init");
+    std::string cmd = argv[1];
+    if (cmd == "prove" && argc == 6) {
+        std::vector<uint8_t> acir, gz, ccs, pk;
+        if (!slurp(argv[3], &gz) || !slurp(argv[4], &ccs) || !slurp(argv[5], &pk)) {
+            fprintf(stderr, "g16prove: cannot read input files\n");
+            return 1;
+        }
+        slurp(argv[2], &acir);  // optional: the .ccs name lists carry the witness mapping
+        g16_circuit* c = nullptr;
+        if (g16_circuit_load(ctx, ccs.data(), ccs.size(), pk.data(), pk.size(), nullptr, &c) != G16_OK) return die("load");
+        uint8_t proof[G16_PROOF_LEN];
+        std::vector<uint8_t> pw(12 + 32 * 4096);
+        size_t pl = sizeof proof, wl = pw.size();
+        if (g16_prove(c, gz.data(), gz.size(), nullptr, proof, &pl, pw.data(), &wl) != G16_OK) return die("prove");
+        std::string base = argv[4];
+        size_t dot = base.rfind('.');
+        if (dot != std::string::npos && base.find('/', dot) == std::string::npos) base.resize(dot);
+        if (!spill(base + ".proof", proof, pl) || !spill(base + ".pw", pw.data(), wl)) {
+            fprintf(stderr, "g16prove: cannot write outputs next to %s\n", argv[4]);
+            return 1;
+        }
+        g16_circuit_free(c);
+    } else if (cmd == "setup" && (argc == 5 || argc == 6)) {
+        std::vector<uint8_t> ccs;
+        if (!slurp(argv[2], &ccs)) {
+            fprintf(stderr, "g16prove: cannot read %s\n", argv[2]);
+            return 1;
+        }
+        std::string seed = argc == 6 ? argv[5] : "";
+        if (seed.empty()) {  // fresh entropy unless a seed is given (tests / reproducible keys)
+            std::vector<uint8_t> rnd;
+            std::ifstream ur("/dev/urandom", std::ios::binary);
+            seed.resize(32);
+            ur.read(&seed[0], 32);
+        }
+        size_t pl = 0, vl = 0;
+        if (g16_setup(ctx, ccs.data(), ccs.size(), (const uint8_t*)seed.data(), seed.size(), nullptr, &pl, nullptr, &vl) != G16_OK)
+            return die("setup");
+        std::vector<uint8_t> pk(pl), vk(vl);
+        if (g16_setup(ctx, ccs.data(), ccs.size(), (const uint8_t*)seed.data(), seed.size(), pk.data(), &pl, vk.data(), &vl) != G16_OK)
+            return die("setup");
+        if (!spill(argv[3], pk.data(), pl) || !spill(argv[4], vk.data(), vl)) {
+            fprintf(stderr, "g16prove: cannot write key files\n");
+            return 1;
+        }
+    } else {
+        fprintf(stderr, "g16prove: bad command line\n");
+        return 2;
+    }
+    g16_shutdown(ctx);
+    return 0;
+}

@@ -17,6 +17,7 @@
 
 #include <atomic>
 #include <fstream>
+#include <future>
 #include <thread>
 
 #include "hostutil.hpp"
@@ -233,7 +234,12 @@ g16_circuit::~g16_circuit() {
     cudaFree(d_coeffs);
     cudaFree(d_mapA); cudaFree(d_mapB); cudaFree(d_mapKZ); cudaFree(d_mapPok);
     cudaFree(d_tmp_g1); cudaFree(d_tmp_g2);
-    if (h_pinned) cudaFreeHost(h_pinned);
+    for (auto& sl : slots) {
+        if (sl.h_wires) cudaFreeHost(sl.h_wires);
+        if (sl.ready) cudaEventDestroy(sl.ready);
+    }
+    g1_aux.release();
+    if (aux_stream) cudaStreamDestroy(aux_stream);
 }
 
 namespace {
@@ -288,11 +294,10 @@ void parallel_for(size_t n, Fn fn) {
     for (auto& x : th) x.join();
 }
 
-// Device part of the pipeline: wires (with the X_* slots filled) are already in c->d_wires.
-int prove_device(g16_circuit* c, size_t B) {
+// Device part of the pipeline: W = B wire vectors (stride wstride, X_* slots filled) in HBM.
+int prove_device(g16_circuit* c, size_t B, const Fr* W) {
     g16_ctx* ctx = c->ctx;
     cudaStream_t st = ctx->stream;
-    const Fr* W = (const Fr*)c->d_wires.ptr;
     Fr* abc = (Fr*)c->d_abc.ptr;
     int launches = 0;
     dim3 grid(cdiv(c->n, 256), 3, (unsigned)B);
@@ -467,14 +472,22 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
     G16_CUDA(cudaMalloc(&c->d_coeffs, sizeof(Fr) * circ.coeffs.size()));
     G16_CUDA(cudaMemcpyAsync(c->d_coeffs, circ.coeffs.data(), sizeof(Fr) * circ.coeffs.size(), cudaMemcpyHostToDevice, st));
     // ---- scratch -------------------------------------------------------------------------------
-    G16_TRY(c->d_wires.ensure(sizeof(Fr) * c->wstride * max_batch));
     G16_TRY(c->d_abc.ensure(sizeof(Fr) * 3 * c->n * max_batch));
-    G16_TRY(c->d_commit_vals.ensure(sizeof(Fr) * (c->n_committed ? c->n_committed : 1) * max_batch));
     G16_TRY(c->d_out.ensure(sizeof(ProofPoints) * max_batch));
+    {
+        int lo = 0, hi = 0;
+        G16_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        G16_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
+    }
+    for (auto& sl : c->slots) {
+        G16_TRY(sl.d_wires.ensure(sizeof(Fr) * c->wstride * max_batch));
+        G16_TRY(sl.d_commit_vals.ensure(sizeof(Fr) * (c->n_committed ? c->n_committed : 1) * max_batch));
+        G16_TRY(sl.d_commit_out.ensure(sizeof(G1Affine) * max_batch));
+        G16_CUDA(cudaMallocHost(&sl.h_wires, sizeof(Fr) * c->wstride * max_batch));
+        G16_CUDA(cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming));
+    }
     G16_CUDA(cudaMalloc(&c->d_tmp_g1, sizeof(G1Affine) * 4 * max_batch));
     G16_CUDA(cudaMalloc(&c->d_tmp_g2, sizeof(G2Affine) * max_batch));
-    c->h_pinned_bytes = sizeof(Fr) * c->wstride * max_batch;
-    G16_CUDA(cudaMallocHost(&c->h_pinned, c->h_pinned_bytes));
     const NttDomain* dom;
     G16_TRY(ctx->ntt.domain(c->logn, st, &dom));
     G16_CUDA(cudaStreamSynchronize(st));
@@ -507,11 +520,12 @@ int g16_prove_wires_dev(g16_circuit* c, size_t n, const void* d_wires, void* d_p
     G16_CUDA(cudaSetDevice(c->ctx->device));
     cudaStream_t st = c->ctx->stream;
     // wires arrive without the X_* slots: lay them out with stride wstride and r = s = 0
-    G16_CUDA(cudaMemsetAsync(c->d_wires.ptr, 0, sizeof(Fr) * c->wstride * n, st));
-    G16_CUDA(cudaMemcpy2DAsync(c->d_wires.ptr, sizeof(Fr) * c->wstride, d_wires, sizeof(Fr) * c->nw,
-                               sizeof(Fr) * c->nw, n, cudaMemcpyDeviceToDevice, st));
-    k_set_one<<<cdiv(n, 128), 128, 0, st>>>((Fr*)c->d_wires.ptr, c->wstride, c->nw + X_ONE, (uint32_t)n);
-    G16_TRY(prove_device(c, n));
+    Fr* W = (Fr*)c->slots[0].d_wires.ptr;
+    G16_CUDA(cudaMemsetAsync(W, 0, sizeof(Fr) * c->wstride * n, st));
+    G16_CUDA(cudaMemcpy2DAsync(W, sizeof(Fr) * c->wstride, d_wires, sizeof(Fr) * c->nw, sizeof(Fr) * c->nw, n,
+                               cudaMemcpyDeviceToDevice, st));
+    k_set_one<<<cdiv(n, 128), 128, 0, st>>>(W, c->wstride, c->nw + X_ONE, (uint32_t)n);
+    G16_TRY(prove_device(c, n, W));
     G16_CUDA(cudaMemcpyAsync(d_proof_points, c->d_out.ptr, sizeof(ProofPoints) * n, cudaMemcpyDeviceToDevice, st));
     return G16_OK;
 }
@@ -522,9 +536,10 @@ static int prove_from_host_wires(g16_circuit* c, size_t n, const HFr* wires, con
                                  uint8_t* proofs) {
     cudaStream_t st = c->ctx->stream;
     size_t bytes = sizeof(Fr) * c->wstride * n;
-    memcpy(c->h_pinned, wires, bytes);
-    G16_CUDA(cudaMemcpyAsync(c->d_wires.ptr, c->h_pinned, bytes, cudaMemcpyHostToDevice, st));
-    G16_TRY(prove_device(c, n));
+    g16_circuit::Slot& sl = c->slots[0];
+    if ((const void*)wires != sl.h_wires) memcpy(sl.h_wires, wires, bytes);
+    G16_CUDA(cudaMemcpyAsync(sl.d_wires.ptr, sl.h_wires, bytes, cudaMemcpyHostToDevice, st));
+    G16_TRY(prove_device(c, n, (const Fr*)sl.d_wires.ptr));
     std::vector<ProofPoints> pts(n);
     G16_CUDA(cudaMemcpyAsync(pts.data(), c->d_out.ptr, sizeof(ProofPoints) * n, cudaMemcpyDeviceToHost, st));
     G16_CUDA(cudaStreamSynchronize(st));
@@ -563,17 +578,107 @@ int g16_prove_wires(g16_circuit* c, size_t n, const uint8_t* wires_be, const uin
             for (size_t b = 0; b < B; b++)
                 for (size_t k = 0; k < c->n_committed; k++) cv[b * c->n_committed + k] = w[b * c->wstride + c->committed_wires[k]];
             cudaStream_t st = c->ctx->stream;
-            G16_CUDA(cudaMemcpyAsync(c->d_commit_vals.ptr, cv.data(), sizeof(Fr) * cv.size(), cudaMemcpyHostToDevice, st));
-            G16_TRY(c->ctx->g1.run(c->bCommit, (const Fr*)c->d_commit_vals.ptr, c->n_committed, nullptr, 1, B, c->d_tmp_g1, st));
+            g16_circuit::Slot& sl = c->slots[0];
+            G16_CUDA(cudaMemcpyAsync(sl.d_commit_vals.ptr, cv.data(), sizeof(Fr) * cv.size(), cudaMemcpyHostToDevice, st));
+            G16_TRY(c->ctx->g1.run(c->bCommit, (const Fr*)sl.d_commit_vals.ptr, c->n_committed, nullptr, 1, B,
+                                   (G1Affine*)sl.d_commit_out.ptr, st));
             size_t nfp = B * 2;
-            k_fp_from_mont<<<cdiv(nfp, 256), 256, 0, st>>>((Fp*)c->d_tmp_g1, nfp);
-            G16_CUDA(cudaMemcpyAsync(commits.data(), c->d_tmp_g1, sizeof(G1Affine) * B, cudaMemcpyDeviceToHost, st));
+            k_fp_from_mont<<<cdiv(nfp, 256), 256, 0, st>>>((Fp*)sl.d_commit_out.ptr, nfp);
+            G16_CUDA(cudaMemcpyAsync(commits.data(), sl.d_commit_out.ptr, sizeof(G1Affine) * B, cudaMemcpyDeviceToHost, st));
             G16_CUDA(cudaStreamSynchronize(st));
         }
         G16_TRY(prove_from_host_wires(c, B, w.data(), c->has_commitment ? commits.data() : nullptr, proofs + plen * done));
         done += B;
     }
     return G16_OK;
+}
+
+// ---- stage A: host solve of one chunk into a pipeline slot (runs on a worker thread) ---------------
+// On success the slot holds: h_wires (Montgomery, X_* slots filled), commits, and an H2D copy of the
+// wires into d_wires has been enqueued on aux_stream with `ready` recorded behind it.
+struct StageResult {
+    int rc = G16_OK;
+    std::string err;
+};
+
+static StageResult stage_solve(g16_circuit* c, int slot_id, size_t B, const uint8_t* assignments_be, const uint8_t* rnd,
+                               size_t first_index, bool upload) {
+    StageResult res;
+    auto failm = [&](int rc, const std::string& m) {
+        res.rc = rc;
+        res.err = m;
+        return res;
+    };
+    auto cuda_fail = [&](cudaError_t e, const char* what) {
+        return failm(G16_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    };
+    cudaError_t ce = cudaSetDevice(c->ctx->device);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
+    const Circuit& circ = c->circ;
+    const size_t nin = circ.nb_public - 1 + circ.nb_secret;
+    g16_circuit::Slot& sl = c->slots[slot_id];
+    cudaStream_t st = c->aux_stream;
+    HFr* W = (HFr*)sl.h_wires;
+    std::vector<SolveState> states(B);
+    std::vector<HFr> rs(3 * B);
+    std::vector<int> rcs(B, G16_OK);
+    for (size_t b = 0; b < B; b++)
+        for (int k = 0; k < 3; k++) {
+            if (rnd) rs[3 * b + k] = HFr::from_be(rnd + 96 * b + 32 * k);
+            else if (random_fr(&rs[3 * b + k]) != G16_OK) return failm(G16_E_INTERNAL, "could not read /dev/urandom");
+        }
+    parallel_for(B, [&](size_t b) {
+        std::vector<HFr> asg(nin);
+        const uint8_t* src = assignments_be + b * nin * 32;
+        for (size_t i = 0; i < nin; i++) asg[i] = HFr::from_be(src + 32 * i);
+        solve_begin(circ, asg.data(), &states[b]);
+        rcs[b] = solve_run(circ, &states[b], &rs[3 * b + 2]);
+    });
+    sl.commits.assign(B, G1Affine::inf());
+    bool any_commit = false;
+    for (size_t b = 0; b < B; b++) {
+        if (rcs[b] == SOLVE_NEED_COMMITMENT) any_commit = true;
+        else if (rcs[b] != SOLVE_DONE) return failm(rcs[b], "proof " + std::to_string(first_index + b) + ": " + states[b].error);
+    }
+    if (any_commit) {
+        std::vector<HFr> cv(c->n_committed * B, HFr::zero());
+        for (size_t b = 0; b < B; b++) {
+            if (rcs[b] != SOLVE_NEED_COMMITMENT || states[b].committed.size() != c->n_committed)
+                return failm(G16_E_INTERNAL, "proof " + std::to_string(first_index + b) + ": inconsistent commitment hint");
+            memcpy(&cv[b * c->n_committed], states[b].committed.data(), sizeof(HFr) * c->n_committed);
+        }
+        if ((ce = cudaMemcpyAsync(sl.d_commit_vals.ptr, cv.data(), sizeof(Fr) * cv.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess)
+            return cuda_fail(ce, "commit H2D");
+        int rc = c->g1_aux.run(c->bCommit, (const Fr*)sl.d_commit_vals.ptr, c->n_committed, nullptr, 1, B,
+                               (G1Affine*)sl.d_commit_out.ptr, st);
+        if (rc != G16_OK) return failm(rc, get_error());
+        k_fp_from_mont<<<cdiv(B * 2, 256), 256, 0, st>>>((Fp*)sl.d_commit_out.ptr, B * 2);
+        if ((ce = cudaMemcpyAsync(sl.commits.data(), sl.d_commit_out.ptr, sizeof(G1Affine) * B, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            return cuda_fail(ce, "commit D2H");
+        if ((ce = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(ce, "commitment MSM");
+        parallel_for(B, [&](size_t b) {
+            std::vector<uint8_t> msg(64 + 32 * states[b].hashed.size());
+            g1_to_be(sl.commits[b], msg.data());
+            for (size_t k = 0; k < states[b].hashed.size(); k++) states[b].hashed[k].to_be(msg.data() + 64 + 32 * k);
+            solve_provide_challenge(&states[b], hash_to_fr(msg.data(), msg.size(), "bsb22-commitment"));
+            rcs[b] = solve_run(circ, &states[b], &rs[3 * b + 2]);
+        });
+        for (size_t b = 0; b < B; b++)
+            if (rcs[b] != SOLVE_DONE)
+                return failm(rcs[b] == SOLVE_NEED_COMMITMENT ? G16_E_HINT : rcs[b],
+                             "proof " + std::to_string(first_index + b) + ": " +
+                                 (rcs[b] == SOLVE_NEED_COMMITMENT ? std::string("more than one commitment") : states[b].error));
+    }
+    parallel_for(B, [&](size_t b) {
+        memcpy(&W[b * c->wstride], states[b].w.data(), sizeof(HFr) * c->nw);
+        fill_extras(&W[b * c->wstride], c->nw, rs[3 * b], rs[3 * b + 1]);
+    });
+    if (upload) {
+        if ((ce = cudaMemcpyAsync(sl.d_wires.ptr, sl.h_wires, sizeof(Fr) * c->wstride * B, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+            return cuda_fail(ce, "wires H2D");
+        if ((ce = cudaEventRecord(sl.ready, st)) != cudaSuccess) return cuda_fail(ce, "event record");
+    }
+    return res;
 }
 
 int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, size_t n_values, const uint8_t* rnd,
@@ -596,81 +701,55 @@ int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, siz
     G16_CUDA(cudaSetDevice(c->ctx->device));
     cudaStream_t st = c->ctx->stream;
     const size_t plen = c->has_commitment ? 388 : 324;
-    for (size_t done = 0; done < n;) {
-        size_t B = std::min(c->max_batch, n - done);
-        std::vector<SolveState> states(B);
-        std::vector<HFr> rs(3 * B);
-        std::vector<int> rcs(B, G16_OK);
-        for (size_t b = 0; b < B; b++)
-            for (int k = 0; k < 3; k++) {
-                if (rnd) rs[3 * b + k] = HFr::from_be(rnd + 96 * (done + b) + 32 * k);
-                else G16_TRY(random_fr(&rs[3 * b + k]));
+    const size_t nchunks = (n + c->max_batch - 1) / c->max_batch;
+    auto chunk_size = [&](size_t k) { return std::min(c->max_batch, n - k * c->max_batch); };
+    auto launch = [&](size_t k) {
+        size_t first = k * c->max_batch;
+        return std::async(std::launch::async, stage_solve, c, (int)(k & 1), chunk_size(k), assignments_be + first * nin * 32,
+                          rnd ? rnd + 96 * first : nullptr, first, true);
+    };
+    std::future<StageResult> fut = launch(0);
+    int total_launches = 0;
+    for (size_t k = 0; k < nchunks; k++) {
+        StageResult sr = fut.get();
+        if (sr.rc != G16_OK) {
+            set_error(sr.err);
+            return sr.rc;
+        }
+        if (k + 1 < nchunks) fut = launch(k + 1);   // the host solves chunk k+1 while the device proves chunk k
+        const size_t B = chunk_size(k), first = k * c->max_batch;
+        g16_circuit::Slot& sl = c->slots[k & 1];
+        int rc = G16_OK;
+        std::vector<ProofPoints> pts(B);
+        do {
+            if (cudaStreamWaitEvent(st, sl.ready, 0) != cudaSuccess) { rc = G16_E_CUDA; set_error("cudaStreamWaitEvent failed"); break; }
+            if ((rc = prove_device(c, B, (const Fr*)sl.d_wires.ptr)) != G16_OK) break;
+            total_launches += c->last_launches;
+            if (cudaMemcpyAsync(pts.data(), c->d_out.ptr, sizeof(ProofPoints) * B, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess) {
+                rc = G16_E_CUDA;
+                set_error(std::string("device pipeline: ") + cudaGetErrorString(cudaGetLastError()));
             }
-        // ---- phase 1: up to the commitment hint
-        parallel_for(B, [&](size_t b) {
-            std::vector<HFr> asg(nin);
-            const uint8_t* src = assignments_be + (done + b) * nin * 32;
-            for (size_t i = 0; i < nin; i++) asg[i] = HFr::from_be(src + 32 * i);
-            solve_begin(circ, asg.data(), &states[b]);
-            rcs[b] = solve_run(circ, &states[b], &rs[3 * b + 2]);
-        });
-        std::vector<G1Affine> commits(B, G1Affine::inf());
-        bool any_commit = false;
+        } while (0);
+        if (rc != G16_OK) {
+            if (k + 1 < nchunks) fut.wait();   // never leave the worker running on freed state
+            return rc;
+        }
+        const HFr* W = (const HFr*)sl.h_wires;
         for (size_t b = 0; b < B; b++) {
-            if (rcs[b] == SOLVE_NEED_COMMITMENT) any_commit = true;
-            else if (rcs[b] != SOLVE_DONE) {
-                set_error("proof " + std::to_string(done + b) + ": " + states[b].error);
-                return rcs[b];
-            }
-        }
-        if (any_commit) {
-            std::vector<HFr> cv(c->n_committed * B, HFr::zero());
-            for (size_t b = 0; b < B; b++) {
-                if (rcs[b] != SOLVE_NEED_COMMITMENT || states[b].committed.size() != c->n_committed) {
-                    set_error("proof " + std::to_string(done + b) + ": inconsistent commitment hint");
-                    return G16_E_INTERNAL;
-                }
-                memcpy(&cv[b * c->n_committed], states[b].committed.data(), sizeof(HFr) * c->n_committed);
-            }
-            G16_CUDA(cudaMemcpyAsync(c->d_commit_vals.ptr, cv.data(), sizeof(Fr) * cv.size(), cudaMemcpyHostToDevice, st));
-            G16_TRY(c->ctx->g1.run(c->bCommit, (const Fr*)c->d_commit_vals.ptr, c->n_committed, nullptr, 1, B, c->d_tmp_g1, st));
-            size_t nfp = B * 2;
-            k_fp_from_mont<<<cdiv(nfp, 256), 256, 0, st>>>((Fp*)c->d_tmp_g1, nfp);
-            G16_CUDA(cudaMemcpyAsync(commits.data(), c->d_tmp_g1, sizeof(G1Affine) * B, cudaMemcpyDeviceToHost, st));
-            G16_CUDA(cudaStreamSynchronize(st));
-            // ---- challenge + phase 2
-            parallel_for(B, [&](size_t b) {
-                std::vector<uint8_t> msg(64 + 32 * states[b].hashed.size());
-                g1_to_be(commits[b], msg.data());
-                for (size_t k = 0; k < states[b].hashed.size(); k++) states[b].hashed[k].to_be(msg.data() + 64 + 32 * k);
-                solve_provide_challenge(&states[b], hash_to_fr(msg.data(), msg.size(), "bsb22-commitment"));
-                rcs[b] = solve_run(circ, &states[b], &rs[3 * b + 2]);
-            });
-            for (size_t b = 0; b < B; b++)
-                if (rcs[b] != SOLVE_DONE) {
-                    set_error("proof " + std::to_string(done + b) + ": " +
-                              (rcs[b] == SOLVE_NEED_COMMITMENT ? std::string("more than one commitment") : states[b].error));
-                    return rcs[b] == SOLVE_NEED_COMMITMENT ? G16_E_HINT : rcs[b];
-                }
-        }
-        std::vector<HFr> w(c->wstride * B);
-        for (size_t b = 0; b < B; b++) {
-            memcpy(&w[b * c->wstride], states[b].w.data(), sizeof(HFr) * c->nw);
-            fill_extras(&w[b * c->wstride], c->nw, rs[3 * b], rs[3 * b + 1]);
-        }
-        G16_TRY(prove_from_host_wires(c, B, w.data(), c->has_commitment ? commits.data() : nullptr, proofs + plen * done));
-        if (pws) {
-            for (size_t b = 0; b < B; b++) {
-                uint8_t* o = pws + pw_stride * (done + b);
+            write_proof_bytes(pts[b], c->has_commitment ? &sl.commits[b] : nullptr, proofs + plen * (first + b));
+            if (pws) {
+                uint8_t* o = pws + pw_stride * (first + b);
                 uint32_t hdr[3] = {(uint32_t)npub, 0, (uint32_t)npub};
-                for (int k = 0; k < 3; k++) {
-                    o[4 * k] = hdr[k] >> 24; o[4 * k + 1] = hdr[k] >> 16; o[4 * k + 2] = hdr[k] >> 8; o[4 * k + 3] = hdr[k];
+                for (int q = 0; q < 3; q++) {
+                    o[4 * q] = hdr[q] >> 24; o[4 * q + 1] = hdr[q] >> 16; o[4 * q + 2] = hdr[q] >> 8; o[4 * q + 3] = hdr[q];
                 }
-                for (size_t i = 0; i < npub; i++) states[b].w[1 + i].to_be(o + 12 + 32 * i);
+                for (size_t i = 0; i < npub; i++) W[b * c->wstride + 1 + i].to_be(o + 12 + 32 * i);
             }
         }
-        done += B;
     }
+    c->last_launches = total_launches;
+    c->ctx->last_launches = total_launches;
     return G16_OK;
 }
 
@@ -692,68 +771,21 @@ int g16_witness_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, s
         set_error("g16_witness_batch: bad arguments");
         return G16_E_ARG;
     }
-    const Circuit& circ = c->circ;
-    const size_t nin = circ.nb_public - 1 + circ.nb_secret;
+    const size_t nin = c->circ.nb_public - 1 + c->circ.nb_secret;
     if (n_values != nin) {
         set_error("g16_witness_batch: assignment size mismatch");
         return G16_E_ARG;
     }
-    G16_CUDA(cudaSetDevice(c->ctx->device));
-    cudaStream_t st = c->ctx->stream;
     for (size_t done = 0; done < n;) {
         size_t B = std::min(c->max_batch, n - done);
-        std::vector<SolveState> states(B);
-        std::vector<HFr> bl(B);
-        std::vector<int> rcs(B, G16_OK);
-        for (size_t b = 0; b < B; b++) {
-            if (rnd) bl[b] = HFr::from_be(rnd + 96 * (done + b) + 64);
-            else G16_TRY(random_fr(&bl[b]));
+        StageResult sr = stage_solve(c, 0, B, assignments_be + done * nin * 32, rnd ? rnd + 96 * done : nullptr, done, false);
+        if (sr.rc != G16_OK) {
+            set_error(sr.err);
+            return sr.rc;
         }
+        const HFr* W = (const HFr*)c->slots[0].h_wires;
         parallel_for(B, [&](size_t b) {
-            std::vector<HFr> asg(nin);
-            const uint8_t* src = assignments_be + (done + b) * nin * 32;
-            for (size_t i = 0; i < nin; i++) asg[i] = HFr::from_be(src + 32 * i);
-            solve_begin(circ, asg.data(), &states[b]);
-            rcs[b] = solve_run(circ, &states[b], &bl[b]);
-        });
-        bool any_commit = false;
-        for (size_t b = 0; b < B; b++) {
-            if (rcs[b] == SOLVE_NEED_COMMITMENT) any_commit = true;
-            else if (rcs[b] != SOLVE_DONE) {
-                set_error("witness " + std::to_string(done + b) + ": " + states[b].error);
-                return rcs[b];
-            }
-        }
-        if (any_commit) {
-            std::vector<HFr> cv(c->n_committed * B, HFr::zero());
-            std::vector<G1Affine> commits(B, G1Affine::inf());
-            for (size_t b = 0; b < B; b++) {
-                if (rcs[b] != SOLVE_NEED_COMMITMENT || states[b].committed.size() != c->n_committed) {
-                    set_error("witness " + std::to_string(done + b) + ": inconsistent commitment hint");
-                    return G16_E_INTERNAL;
-                }
-                memcpy(&cv[b * c->n_committed], states[b].committed.data(), sizeof(HFr) * c->n_committed);
-            }
-            G16_CUDA(cudaMemcpyAsync(c->d_commit_vals.ptr, cv.data(), sizeof(Fr) * cv.size(), cudaMemcpyHostToDevice, st));
-            G16_TRY(c->ctx->g1.run(c->bCommit, (const Fr*)c->d_commit_vals.ptr, c->n_committed, nullptr, 1, B, c->d_tmp_g1, st));
-            k_fp_from_mont<<<cdiv(B * 2, 256), 256, 0, st>>>((Fp*)c->d_tmp_g1, B * 2);
-            G16_CUDA(cudaMemcpyAsync(commits.data(), c->d_tmp_g1, sizeof(G1Affine) * B, cudaMemcpyDeviceToHost, st));
-            G16_CUDA(cudaStreamSynchronize(st));
-            parallel_for(B, [&](size_t b) {
-                std::vector<uint8_t> msg(64 + 32 * states[b].hashed.size());
-                g1_to_be(commits[b], msg.data());
-                for (size_t k = 0; k < states[b].hashed.size(); k++) states[b].hashed[k].to_be(msg.data() + 64 + 32 * k);
-                solve_provide_challenge(&states[b], hash_to_fr(msg.data(), msg.size(), "bsb22-commitment"));
-                rcs[b] = solve_run(circ, &states[b], &bl[b]);
-            });
-            for (size_t b = 0; b < B; b++)
-                if (rcs[b] != SOLVE_DONE) {
-                    set_error("witness " + std::to_string(done + b) + ": " + states[b].error);
-                    return rcs[b] == SOLVE_NEED_COMMITMENT ? G16_E_HINT : rcs[b];
-                }
-        }
-        parallel_for(B, [&](size_t b) {
-            for (size_t i = 0; i < c->nw; i++) states[b].w[i].to_be(wires_be + ((done + b) * c->nw + i) * 32);
+            for (size_t i = 0; i < c->nw; i++) W[b * c->wstride + i].to_be(wires_be + ((done + b) * c->nw + i) * 32);
         });
         done += B;
     }

@@ -64,11 +64,19 @@ struct g16_circuit {
     uint32_t *d_mapA = nullptr, *d_mapB = nullptr, *d_mapKZ = nullptr, *d_mapPok = nullptr;
     size_t nA = 0, nB = 0, nK = 0, nZ = 0;
     // scratch sized for max_batch proofs
-    g16::DeviceBuf d_wires, d_abc, d_commit_vals, d_out;
+    g16::DeviceBuf d_abc, d_out;
     g16::G1Affine* d_tmp_g1 = nullptr;   // [4][max_batch]: A, B1, KZ, PoK results (Montgomery)
     g16::G2Affine* d_tmp_g2 = nullptr;   // [max_batch]
-    void* h_pinned = nullptr;            // staging for wires / results
-    size_t h_pinned_bytes = 0;
+    // Two pipeline slots: while the device proves chunk k out of slot k%2, the host solves chunk
+    // k+1 into the other slot (its commitment MSM runs on `aux_stream` with its own MSM scratch).
+    struct Slot {
+        g16::DeviceBuf d_wires, d_commit_vals, d_commit_out;
+        void* h_wires = nullptr;         // pinned, max_batch * wstride Fr
+        cudaEvent_t ready = nullptr;     // wires of this slot are in d_wires
+        std::vector<g16::G1Affine> commits;
+    } slots[2];
+    cudaStream_t aux_stream = nullptr;
+    g16::MsmRunner<g16::Fp> g1_aux;
     int last_launches = 0;
     ~g16_circuit();
 };
