@@ -239,7 +239,14 @@ g16_circuit::~g16_circuit() {
         if (sl.ready) cudaEventDestroy(sl.ready);
     }
     g1_aux.release();
+    g1_side.release();
+    g2_side.release();
     if (aux_stream) cudaStreamDestroy(aux_stream);
+    for (int i = 0; i < 2; i++) {
+        if (side[i]) cudaStreamDestroy(side[i]);
+        if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+    }
+    if (ev_fork) cudaEventDestroy(ev_fork);
 }
 
 namespace {
@@ -300,6 +307,11 @@ int prove_device(g16_circuit* c, size_t B, const Fr* W) {
     cudaStream_t st = ctx->stream;
     Fr* abc = (Fr*)c->d_abc.ptr;
     int launches = 0;
+    if (!ctx->prof.enabled) {   // side streams start once the wires are in place
+        G16_CUDA(cudaEventRecord(c->ev_fork, st));
+        G16_CUDA(cudaStreamWaitEvent(c->side[0], c->ev_fork, 0));
+        G16_CUDA(cudaStreamWaitEvent(c->side[1], c->ev_fork, 0));
+    }
     dim3 grid(cdiv(c->n, 256), 3, (unsigned)B);
     k_r1cs_spmv<<<grid, 256, 0, st>>>(c->d_rowptr[0], c->d_cid[0], c->d_wid[0], c->d_rowptr[1], c->d_cid[1],
                                       c->d_wid[1], c->d_rowptr[2], c->d_cid[2], c->d_wid[2], c->d_coeffs, W,
@@ -312,19 +324,29 @@ int prove_device(g16_circuit* c, size_t B, const Fr* W) {
     G1Affine* rB1 = c->d_tmp_g1 + c->max_batch;
     G1Affine* rKZ = c->d_tmp_g1 + 2 * c->max_batch;
     G1Affine* rPok = c->d_tmp_g1 + 3 * c->max_batch;
-    G16_TRY(ctx->g1.run(c->bA, W, c->wstride, c->d_mapA, 1, B, rA, st));
-    launches += ctx->g1.launches;
-    G16_TRY(ctx->g1.run(c->bB1, W, c->wstride, c->d_mapB, 1, B, rB1, st));
-    launches += ctx->g1.launches;
-    G16_TRY(ctx->g2.run(c->bB2, W, c->wstride, c->d_mapB, 1, B, c->d_tmp_g2, st));
-    launches += ctx->g2.launches;
+    // per-kernel profiling wants serial, un-overlapped launches
+    const bool overlap = !ctx->prof.enabled;
+    cudaStream_t s1 = overlap ? c->side[0] : st, s2 = overlap ? c->side[1] : st;
+    c->g1_side.prof = c->g2_side.prof = &ctx->prof;
+    G16_TRY(c->g1_side.run(c->bA, W, c->wstride, c->d_mapA, 1, B, rA, s1));
+    launches += c->g1_side.launches;
+    G16_TRY(c->g1_side.run(c->bB1, W, c->wstride, c->d_mapB, 1, B, rB1, s1));
+    launches += c->g1_side.launches;
+    if (c->has_commitment) {
+        G16_TRY(c->g1_side.run(c->bPok, W, c->wstride, c->d_mapPok, 1, B, rPok, s1));
+        launches += c->g1_side.launches;
+    } else {
+        G16_CUDA(cudaMemsetAsync(rPok, 0, sizeof(G1Affine) * B, s1));
+    }
+    G16_TRY(c->g2_side.run(c->bB2, W, c->wstride, c->d_mapB, 1, B, c->d_tmp_g2, s2));
+    launches += c->g2_side.launches;
     G16_TRY(ctx->g1.run(c->bKZ, W, c->wstride, c->d_mapKZ, 1, B, rKZ, st, abc, 3 * c->n));
     launches += ctx->g1.launches;
-    if (c->has_commitment) {
-        G16_TRY(ctx->g1.run(c->bPok, W, c->wstride, c->d_mapPok, 1, B, rPok, st));
-        launches += ctx->g1.launches;
-    } else {
-        G16_CUDA(cudaMemsetAsync(rPok, 0, sizeof(G1Affine) * B, st));
+    if (overlap) {
+        G16_CUDA(cudaEventRecord(c->ev_join[0], s1));
+        G16_CUDA(cudaEventRecord(c->ev_join[1], s2));
+        G16_CUDA(cudaStreamWaitEvent(st, c->ev_join[0], 0));
+        G16_CUDA(cudaStreamWaitEvent(st, c->ev_join[1], 0));
     }
     k_finalize<<<(unsigned)B, 32, 0, st>>>(rA, rB1, c->d_tmp_g2, rKZ, rPok, W, c->wstride, c->nw,
                                            (ProofPoints*)c->d_out.ptr);
@@ -479,6 +501,11 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
         G16_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         G16_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
     }
+    for (int i = 0; i < 2; i++) {
+        G16_CUDA(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+        G16_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+    G16_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (auto& sl : c->slots) {
         G16_TRY(sl.d_wires.ensure(sizeof(Fr) * c->wstride * max_batch));
         G16_TRY(sl.d_commit_vals.ensure(sizeof(Fr) * (c->n_committed ? c->n_committed : 1) * max_batch));

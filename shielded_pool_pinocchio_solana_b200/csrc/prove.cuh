@@ -77,6 +77,13 @@ struct g16_circuit {
     } slots[2];
     cudaStream_t aux_stream = nullptr;
     g16::MsmRunner<g16::Fp> g1_aux;
+    // The MSMs that only need the wires (A, B1, PoK on side[0]; B2 on side[1]) run on side streams
+    // next to SpMV -> H -> K|Z on the context stream: the latency-bound tails of one MSM (scan,
+    // ordering, bucket reduction) hide under another MSM's accumulation.
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    g16::MsmRunner<g16::Fp> g1_side;
+    g16::MsmRunner<g16::Fp2> g2_side;
     int last_launches = 0;
     ~g16_circuit();
 };
