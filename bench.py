@@ -88,7 +88,8 @@ class CpuReference:
         import ccs as occs
         import coracle
         import groth16 as G
-        self.cores = coracle.set_threads(0)
+        # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+        self.cores = coracle.set_threads(os.cpu_count() or 1)
         c = occs.parse_ccs(ccs_bytes)
         self.cc = coracle.CCircuit(c, G.read_pk(pk_bytes, c))
         self.k = 0
@@ -127,6 +128,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    # host solver threads per rank: the box's cores are shared by all ranks
+    os.environ.setdefault("G16_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world))))
     ctx = g16.Context(local)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -257,7 +260,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": results["dev"] / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs, IMAD.WIDE)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "proofs_per_step_per_gpu": B,
+            "config": {"workload": WORKLOAD, "proofs_per_step_per_gpu": B, "witness_solver": circ.solver,
                        "l2": "inputs larger than L2 (per-step working set > 400 MB), two input sets alternated",
                        "windows": {k: circ.info[k] for k in ("window_a", "window_b1", "window_kz", "window_b2")}},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * (wstride * 32 + circ.info["n_committed"] * 32),

@@ -117,6 +117,9 @@ int g16_compute_h_dev(g16_ctx* ctx, void* d_abc, unsigned logn, size_t nproofs);
 int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uint8_t* pk, size_t pk_len,
                      const char* acir_json, g16_circuit** out);
 void g16_circuit_free(g16_circuit* c);
+/* "gpu" when witnesses of this circuit are solved by the batched device solver; otherwise the
+ * reason the host solver is used (an unimplemented hint, G16_HOST_SOLVER set, ...). */
+const char* g16_circuit_solver(const g16_circuit* c);
 /* sizes: what[0]=nbConstraints [1]=nbWires [2]=nbPublic(incl. ONE) [3]=nbSecret [4]=domain size
  *        [5]=nbCommitments [6..10] = MSM sizes A,B,K,Z,commit [11]=max proofs per device batch
  *        [12..15] = window bits chosen for the A, B1, K+Z and B2 MSMs */

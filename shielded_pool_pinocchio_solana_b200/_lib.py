@@ -54,6 +54,7 @@ PROTOTYPES = {
     "g16_fr_to_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p]),
     "g16_witness_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
                                          ctypes.c_char_p, ctypes.c_char_p]),
+    "g16_circuit_solver": (ctypes.c_char_p, [ctypes.c_void_p]),
     "g16_circuit_free": (None, [ctypes.c_void_p]),
     "g16_circuit_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]),
     "g16_prove": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_char_p,

@@ -151,6 +151,7 @@ class Circuit:
         self.proof_len = 388 if self.info["nb_commitments"] else 324
         self.pw_len = 12 + 32 * (self.info["nb_public"] - 1)
         self.n_values = self.info["nb_public"] - 1 + self.info["nb_secret"]
+        self.solver = ctx.lib.g16_circuit_solver(self.handle).decode()
 
     def free(self):
         if self.handle:

@@ -1,0 +1,359 @@
+// gpusolver.cu -- the R1CS witness solve (gnark `constraint/bn254/solver.go`, SURVEY.md 3.2 step 1,
+// 8a row a3, 8(f) rank 1) on the GPU, for a whole batch of proofs at once.
+//
+// gnark walks the instruction levels with goroutines; on a 16-core host that costs 10-20 ms per
+// audit-size proof and caps a box at a few hundred proofs/s -- less than ONE B200 proves.  Here the
+// level structure is compiled once per circuit into a static plan (which wire each row defines is
+// independent of the witness), and a CTA per proof executes it: threads take the instructions of a
+// level, __syncthreads() separates levels, wires live in HBM in the layout the prover reads.
+// The BSB22 commitment splits the plan in two phases (prove.cu runs the commitment MSM between).
+// Circuits using a hint this file does not implement keep the host solver (solver.cpp).
+#include "gpusolver.cuh"
+
+#include <string.h>
+
+namespace g16 {
+
+namespace {
+
+constexpr uint32_t NO_WIRE = 0xFFFFFFFEu;
+constexpr int SOLVE_THREADS = 128;
+
+__device__ __forceinline__ Fr lin_eval(const uint32_t* __restrict__ terms, uint32_t n, const Fr* __restrict__ w,
+                                       const Fr* __restrict__ coeffs, uint32_t skip, int unit_ids) {
+    Fr acc = Fr::zero();
+    for (uint32_t k = 0; k < n; k++) {
+        uint32_t cid = terms[2 * k], wid = terms[2 * k + 1];
+        if (wid == skip) continue;
+        if (wid == CCS_CONST_WIRE) {
+            acc = acc + coeffs[cid];
+            continue;
+        }
+        Fr x = w[wid];
+        if (unit_ids && cid == 1) acc = acc + x;
+        else if (unit_ids && cid == 3) acc = acc - x;
+        else if (!(unit_ids && cid == 0)) acc = acc + coeffs[cid] * x;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ uint32_t canon_bits(const Fr& c, uint32_t lo, uint32_t nbits) {
+    // bits [lo, lo+nbits) of a canonical 256-bit value, nbits <= 32
+    if (lo >= 256) return 0;
+    uint32_t wi = lo >> 5, sh = lo & 31;
+    uint64_t v = c.v[wi];
+    if (wi + 1 < 8) v |= (uint64_t)c.v[wi + 1] << 32;
+    v >>= sh;
+    return nbits >= 32 ? (uint32_t)v : (uint32_t)v & ((1u << nbits) - 1u);
+}
+
+__device__ __forceinline__ Fr fr_from_u32(uint32_t x) {
+    Fr f = Fr::zero();
+    f.v[0] = x;
+    return f.to_mont();
+}
+
+__device__ void run_hint(uint32_t kind, const uint32_t* __restrict__ cd, Fr* __restrict__ w,
+                         const Fr* __restrict__ coeffs, int unit_ids, const Fr& blinder, uint32_t* err) {
+    const uint32_t nin = cd[2];
+    // locate the output range: walk the input expressions
+    uint32_t p = 3;
+    for (uint32_t i = 0; i < nin; i++) p += 1 + 2 * cd[p];
+    const uint32_t o0 = cd[p], o1 = cd[p + 1], nout = o1 - o0;
+    auto input = [&](uint32_t idx) {
+        uint32_t q = 3;
+        for (uint32_t i = 0; i < idx; i++) q += 1 + 2 * cd[q];
+        return lin_eval(cd + q + 1, cd[q], w, coeffs, NO_WIRE, unit_ids);
+    };
+    switch (kind) {
+        case HINT_NBITS: {
+            Fr c = input(0).from_mont();
+            for (uint32_t k = 0; k < nout; k++) w[o0 + k] = fr_from_u32(canon_bits(c, k, 1));
+            break;
+        }
+        case HINT_INVZERO:
+            w[o0] = input(0).inverse();
+            break;
+        case HINT_DECOMPOSE: {
+            Fr ls = input(1).from_mont(), c = input(2).from_mont();
+            uint32_t limb = ls.v[0];
+            if (limb == 0 || limb > 32 || (ls.v[1] | ls.v[2] | ls.v[3] | ls.v[4] | ls.v[5] | ls.v[6] | ls.v[7])) {
+                atomicMin(err, 0x80000000u | 1u);
+                break;
+            }
+            for (uint32_t k = 0; k < nout; k++) w[o0 + k] = fr_from_u32(canon_bits(c, k * limb, limb));
+            break;
+        }
+        case HINT_COUNT: {
+            // logderivarg.countHint with one column: out[j] = #queries equal to table row j
+            Fr a = input(0).from_mont();
+            uint32_t size = a.v[0];
+            for (uint32_t k = 0; k < nout; k++) w[o0 + k] = Fr::zero();
+            // table rows are inputs 2..2+size, queries follow; walk the expressions once
+            uint32_t q = 3;
+            for (uint32_t i = 0; i < 2; i++) q += 1 + 2 * cd[q];
+            uint32_t table_q = q;
+            for (uint32_t i = 0; i < size; i++) q += 1 + 2 * cd[q];
+            Fr one = Fr::one();
+            for (uint32_t qi = 2 + size; qi < nin; qi++) {
+                Fr val = lin_eval(cd + q + 1, cd[q], w, coeffs, NO_WIRE, unit_ids);
+                q += 1 + 2 * cd[q];
+                uint32_t t = table_q;
+                bool found = false;
+                for (uint32_t j = 0; j < size; j++) {
+                    Fr row = lin_eval(cd + t + 1, cd[t], w, coeffs, NO_WIRE, unit_ids);
+                    t += 1 + 2 * cd[t];
+                    if (row == val) {
+                        w[o0 + j] = w[o0 + j] + one;
+                        found = true;
+                        break;
+                    }
+                }
+                if (!found) atomicMin(err, 0x80000000u | 2u);
+            }
+            break;
+        }
+        case HINT_RANDOMIZE:
+            for (uint32_t k = 0; k < nout; k++) w[o0 + k] = blinder;
+            break;
+        default:
+            atomicMin(err, 0x80000000u | 3u);
+    }
+}
+
+// One CTA per proof; levels [lvl_begin, lvl_end).
+__global__ void __launch_bounds__(SOLVE_THREADS)
+k_solve_levels(const uint32_t* __restrict__ lvl_off, const uint32_t* __restrict__ lvl_instr,
+               const uint4* __restrict__ info, const uint32_t* __restrict__ instr_cd,
+               const uint32_t* __restrict__ calldata, const Fr* __restrict__ coeffs,
+               const Fr* __restrict__ coeff_invs, Fr* __restrict__ wires, size_t wstride, size_t blinder_slot,
+               uint32_t lvl_begin, uint32_t lvl_end, int unit_ids, uint32_t* __restrict__ err) {
+    const uint32_t b = blockIdx.x;
+    Fr* w = wires + (size_t)b * wstride;
+    uint32_t* e = err + b;
+    for (uint32_t lv = lvl_begin; lv < lvl_end; lv++) {
+        const uint32_t s = lvl_off[lv], t = lvl_off[lv + 1];
+        for (uint32_t k = s + threadIdx.x; k < t; k += SOLVE_THREADS) {
+            const uint32_t ins = lvl_instr[k];
+            const uint4 inf = info[ins];
+            const uint32_t* cd = calldata + instr_cd[ins];
+            if (inf.x >= 16) {
+                run_hint(inf.x - 16, cd, w, coeffs, unit_ids, w[blinder_slot], e);
+                continue;
+            }
+            const uint32_t nl = cd[1], nr = cd[2], no = cd[3];
+            const uint32_t skip = inf.x == 0 ? NO_WIRE : inf.y;
+            Fr L = lin_eval(cd + 4, nl, w, coeffs, skip, unit_ids);
+            Fr Rr = lin_eval(cd + 4 + 2 * nl, nr, w, coeffs, skip, unit_ids);
+            Fr O = lin_eval(cd + 4 + 2 * (nl + nr), no, w, coeffs, skip, unit_ids);
+            if (inf.x == 0) {
+                if (L * Rr != O) atomicMin(e, inf.w + 1);           // constraint row (1-based)
+            } else if (inf.x == 1) {
+                w[inf.y] = (L * Rr - O) * coeff_invs[inf.z];
+            } else if (inf.x == 2) {
+                if (Rr.is_zero()) atomicMin(e, inf.w + 1);
+                else w[inf.y] = (O * Rr.inverse() - L) * coeff_invs[inf.z];
+            } else {
+                if (L.is_zero()) atomicMin(e, inf.w + 1);
+                else w[inf.y] = (O * L.inverse() - Rr) * coeff_invs[inf.z];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// assignment (big-endian canonical) -> wires[b][1..nin] (Montgomery), wire 0 = 1, X_* slots from rnd
+__global__ void __launch_bounds__(256)
+k_assign(const uint8_t* __restrict__ asg_be, const uint8_t* __restrict__ rnd_be, uint32_t nin, Fr* __restrict__ wires,
+         size_t wstride, size_t nw) {
+    const uint32_t b = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    Fr* w = wires + (size_t)b * wstride;
+    auto load_be = [](const uint8_t* p) {
+        Fr f;
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+            const uint8_t* q = p + 28 - 4 * l;
+            f.v[l] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+        }
+        // reduce values >= r (inputs are 256-bit): at most 5 subtractions
+        uint32_t m[8], d[8];
+        Fr::modulus(m);
+        for (int it = 0; it < 6; it++) {
+            if (ff_sub8(d, f.v, m)) break;
+#pragma unroll
+            for (int l = 0; l < 8; l++) f.v[l] = d[l];
+        }
+        return f.to_mont();
+    };
+    if (i < nin) w[1 + i] = load_be(asg_be + ((size_t)b * nin + i) * 32);
+    if (i == 0) {
+        w[0] = Fr::one();
+        Fr r = load_be(rnd_be + (size_t)b * 96), s = load_be(rnd_be + (size_t)b * 96 + 32),
+           bl = load_be(rnd_be + (size_t)b * 96 + 64);
+        w[nw + X_ONE] = Fr::one();
+        w[nw + X_R] = r;
+        w[nw + X_S] = s;
+        w[nw + X_NEG_RS] = (r * s).neg();
+        w[nw + X_BLINDER] = bl;
+        for (int k = X_BLINDER + 1; k < X_COUNT; k++) w[nw + k] = Fr::zero();
+    }
+}
+
+__global__ void k_set_wire(Fr* wires, size_t wstride, uint32_t wire, const Fr* __restrict__ values, uint32_t n) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n) wires[(size_t)b * wstride + wire] = values[b];
+}
+
+template <class T>
+int upload(const std::vector<T>& v, T** d, cudaStream_t st) {
+    G16_CUDA(cudaMalloc(d, sizeof(T) * (v.size() ? v.size() : 1)));
+    if (!v.empty()) G16_CUDA(cudaMemcpyAsync(*d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, st));
+    return G16_OK;
+}
+
+}  // namespace
+
+void GpuSolverPlan::release() {
+    cudaFree(d_lvl_off); cudaFree(d_lvl_instr); cudaFree(d_info); cudaFree(d_instr_cd); cudaFree(d_calldata);
+    cudaFree(d_coeff_invs);
+    d_lvl_off = d_lvl_instr = d_instr_cd = d_calldata = nullptr;
+    d_info = nullptr;
+    d_coeff_invs = nullptr;
+    valid = false;
+}
+
+int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not) {
+    release();
+    const uint32_t nw = c.nb_wires();
+    std::vector<uint8_t> known(nw, 0);
+    for (uint32_t i = 0; i < c.nb_public + c.nb_secret; i++) known[i] = 1;
+    const size_t ninstr = c.blueprint.size();
+    std::vector<uint4> info(ninstr, make_uint4(0, 0, 0, 0));
+    std::vector<uint32_t> lvl_off(1, 0), lvl_instr, instr_cd(ninstr);
+    for (size_t i = 0; i < ninstr; i++) {
+        if (c.start_calldata[i] > 0xffffffffull) {
+            *why_not = "calldata larger than 2^32 words";
+            return G16_OK;
+        }
+        instr_cd[i] = (uint32_t)c.start_calldata[i];
+    }
+    commit_level = (uint32_t)-1;
+    size_t commits_seen = 0;
+    for (size_t lv = 0; lv < c.levels.size(); lv++) {
+        std::vector<uint32_t> newly;
+        for (uint32_t ins : c.levels[lv]) {
+            const uint32_t* cd = c.calldata.data() + c.start_calldata[ins];
+            if (c.blueprint[ins] == 1) {
+                uint32_t cnt[3] = {cd[1], cd[2], cd[3]};
+                uint32_t unk = NO_WIRE, unk_terms = 0, unk_side = 0, unk_cid = 0;
+                size_t p = 4;
+                bool multi = false;
+                for (int side = 0; side < 3; side++)
+                    for (uint32_t k = 0; k < cnt[side]; k++, p += 2) {
+                        uint32_t wid = cd[p + 1];
+                        if (wid == CCS_CONST_WIRE || known[wid]) continue;
+                        if (unk != NO_WIRE && wid != unk) multi = true;
+                        unk = wid;
+                        unk_terms++;
+                        unk_side = side;
+                        unk_cid = cd[p];
+                    }
+                if (multi || unk_terms > 1) {
+                    *why_not = "a row defines its wire through more than one term";
+                    return G16_OK;
+                }
+                uint32_t mode = unk == NO_WIRE ? 0 : (unk_side == 2 ? 1 : (unk_side == 0 ? 2 : 3));
+                info[ins] = make_uint4(mode, unk, unk_cid, c.constraint_offset[ins]);
+                if (unk != NO_WIRE) newly.push_back(unk);
+                lvl_instr.push_back(ins);
+            } else {
+                uint32_t hid = cd[1], nin = cd[2];
+                auto kit = c.hint_kinds.find(hid);
+                HintKind kind = kit == c.hint_kinds.end() ? HINT_UNKNOWN : kit->second;
+                size_t p = 3;
+                for (uint32_t i = 0; i < nin; i++) p += 1 + 2 * (size_t)cd[p];
+                uint32_t o0 = cd[p], o1 = cd[p + 1];
+                for (uint32_t wv = o0; wv < o1 && wv < nw; wv++) newly.push_back(wv);
+                if (kind == HINT_COMMIT) {
+                    if (commits_seen++ || c.commitments.empty()) {
+                        *why_not = "more than one commitment";
+                        return G16_OK;
+                    }
+                    if (!c.commitments[0].public_and_commitment_committed.empty()) {
+                        *why_not = "commitment hashes public wires (not needed by the reference circuits)";
+                        return G16_OK;
+                    }
+                    commit_level = (uint32_t)lv;
+                    commit_wire = o0;
+                    continue;   // executed by prove.cu between the two phases
+                }
+                if (kind == HINT_UNKNOWN) {
+                    auto nm = c.hint_names.find(hid);
+                    *why_not = "hint without a device implementation: " + (nm == c.hint_names.end() ? std::to_string(hid) : nm->second);
+                    return G16_OK;
+                }
+                if (kind == HINT_COUNT) {
+                    // device version handles the one-column form only (what rangecheck emits)
+                    // nbCols is input 1: a constant expression
+                    size_t q = 3 + 1 + 2 * (size_t)cd[3];
+                    bool ok = cd[q] == 1 && cd[q + 2] == CCS_CONST_WIRE;
+                    if (ok) {
+                        HFr one = HFr::one();
+                        ok = c.coeffs[cd[q + 1]] == one;
+                    }
+                    if (!ok) {
+                        *why_not = "countHint with more than one column";
+                        return G16_OK;
+                    }
+                }
+                info[ins] = make_uint4(16 + (uint32_t)kind, 0, 0, 0);
+                lvl_instr.push_back(ins);
+            }
+        }
+        for (uint32_t wv : newly) known[wv] = 1;
+        lvl_off.push_back((uint32_t)lvl_instr.size());
+    }
+    for (uint32_t i = 0; i < nw; i++)
+        if (!known[i]) {
+            *why_not = "wire " + std::to_string(i) + " is never defined";
+            return G16_OK;
+        }
+    nlevels = (uint32_t)c.levels.size();
+    G16_TRY(upload(lvl_off, &d_lvl_off, st));
+    G16_TRY(upload(lvl_instr, &d_lvl_instr, st));
+    G16_TRY(upload(info, &d_info, st));
+    G16_TRY(upload(instr_cd, &d_instr_cd, st));
+    G16_TRY(upload(c.calldata, &d_calldata, st));
+    G16_CUDA(cudaMalloc(&d_coeff_invs, sizeof(Fr) * c.coeff_invs.size()));
+    G16_CUDA(cudaMemcpyAsync(d_coeff_invs, c.coeff_invs.data(), sizeof(Fr) * c.coeff_invs.size(), cudaMemcpyHostToDevice, st));
+    G16_CUDA(cudaStreamSynchronize(st));
+    valid = true;
+    return G16_OK;
+}
+
+int GpuSolverPlan::assign(const uint8_t* d_asg_be, const uint8_t* d_rnd_be, uint32_t nin, Fr* d_wires, size_t wstride,
+                          size_t nw, size_t B, cudaStream_t st) const {
+    dim3 grid(cdiv(nin ? nin : 1, 256), (unsigned)B);
+    k_assign<<<grid, 256, 0, st>>>(d_asg_be, d_rnd_be, nin, d_wires, wstride, nw);
+    G16_CUDA(cudaGetLastError());
+    return G16_OK;
+}
+
+int GpuSolverPlan::run(const Fr* d_coeffs, int unit_ids, Fr* d_wires, size_t wstride, size_t nw, size_t B,
+                       uint32_t lvl_begin, uint32_t lvl_end, uint32_t* d_err, cudaStream_t st) const {
+    if (lvl_begin >= lvl_end) return G16_OK;
+    k_solve_levels<<<(unsigned)B, SOLVE_THREADS, 0, st>>>(d_lvl_off, d_lvl_instr, d_info, d_instr_cd, d_calldata, d_coeffs,
+                                                          d_coeff_invs, d_wires, wstride, nw + X_BLINDER, lvl_begin,
+                                                          lvl_end, unit_ids, d_err);
+    G16_CUDA(cudaGetLastError());
+    return G16_OK;
+}
+
+int GpuSolverPlan::set_wire(Fr* d_wires, size_t wstride, uint32_t wire, const Fr* d_values, size_t B, cudaStream_t st) const {
+    k_set_wire<<<cdiv(B, 128), 128, 0, st>>>(d_wires, wstride, wire, d_values, (uint32_t)B);
+    G16_CUDA(cudaGetLastError());
+    return G16_OK;
+}
+
+}  // namespace g16

@@ -1,0 +1,36 @@
+// gpusolver.cuh -- batched R1CS witness solver on the GPU (see gpusolver.cu).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "ccs.hpp"
+#include "common.cuh"
+#include "ff.cuh"
+
+namespace g16 {
+
+// slots appended to every proof's wire vector on the device
+enum { X_ONE = 0, X_R = 1, X_S = 2, X_NEG_RS = 3, X_BLINDER = 4, X_COUNT = 8 };
+
+struct GpuSolverPlan {
+    bool valid = false;
+    uint32_t nlevels = 0;
+    uint32_t commit_level = (uint32_t)-1;   // level holding the BSB22 commitment hint, or -1
+    uint32_t commit_wire = 0;
+    uint32_t *d_lvl_off = nullptr, *d_lvl_instr = nullptr, *d_instr_cd = nullptr, *d_calldata = nullptr;
+    uint4* d_info = nullptr;
+    Fr* d_coeff_invs = nullptr;
+
+    // Compiles the plan; leaves valid == false (and says why) when the circuit needs the host solver.
+    int build(const Circuit& c, cudaStream_t st, std::string* why_not);
+    // big-endian assignments / (r,s,blinder) triples already on the device -> wires
+    int assign(const uint8_t* d_asg_be, const uint8_t* d_rnd_be, uint32_t nin, Fr* d_wires, size_t wstride, size_t nw,
+               size_t B, cudaStream_t st) const;
+    int run(const Fr* d_coeffs, int unit_ids, Fr* d_wires, size_t wstride, size_t nw, size_t B, uint32_t lvl_begin,
+            uint32_t lvl_end, uint32_t* d_err, cudaStream_t st) const;
+    int set_wire(Fr* d_wires, size_t wstride, uint32_t wire, const Fr* d_values, size_t B, cudaStream_t st) const;
+    void release();
+    ~GpuSolverPlan() { release(); }
+};
+
+}  // namespace g16

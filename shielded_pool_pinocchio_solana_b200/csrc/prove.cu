@@ -234,7 +234,9 @@ g16_circuit::~g16_circuit() {
     cudaFree(d_coeffs);
     cudaFree(d_mapA); cudaFree(d_mapB); cudaFree(d_mapKZ); cudaFree(d_mapPok);
     cudaFree(d_tmp_g1); cudaFree(d_tmp_g2);
+    cudaFree(d_map_commit);
     for (auto& sl : slots) {
+        if (sl.h_stage) cudaFreeHost(sl.h_stage);
         if (sl.h_wires) cudaFreeHost(sl.h_wires);
         if (sl.ready) cudaEventDestroy(sl.ready);
     }
@@ -281,6 +283,10 @@ int random_fr(HFr* out) {
 }
 
 size_t default_threads() {
+    if (const char* e = getenv("G16_HOST_THREADS")) {
+        long v = atol(e);
+        if (v > 0) return (size_t)v;
+    }
     unsigned hc = std::thread::hardware_concurrency();
     return hc ? hc : 4;
 }
@@ -512,6 +518,18 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
         G16_TRY(sl.d_commit_out.ensure(sizeof(G1Affine) * max_batch));
         G16_CUDA(cudaMallocHost(&sl.h_wires, sizeof(Fr) * c->wstride * max_batch));
         G16_CUDA(cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming));
+        const size_t nin = circ.nb_public - 1 + circ.nb_secret;
+        G16_TRY(sl.d_asg_be.ensure(32 * nin * max_batch));
+        G16_TRY(sl.d_rnd_be.ensure(96 * max_batch));
+        G16_TRY(sl.d_err.ensure(4 * max_batch));
+        G16_TRY(sl.d_chal.ensure(sizeof(Fr) * max_batch));
+        G16_CUDA(cudaMallocHost(&sl.h_stage, (32 * nin + 96 + sizeof(Fr) + 4) * max_batch));
+    }
+    G16_TRY(upload_vec(c->committed_wires, &c->d_map_commit, st));
+    if (!getenv("G16_HOST_SOLVER")) {
+        G16_TRY(c->plan.build(circ, st, &c->host_solver_reason));
+    } else {
+        c->host_solver_reason = "G16_HOST_SOLVER is set";
     }
     G16_CUDA(cudaMalloc(&c->d_tmp_g1, sizeof(G1Affine) * 4 * max_batch));
     G16_CUDA(cudaMalloc(&c->d_tmp_g2, sizeof(G2Affine) * max_batch));
@@ -523,6 +541,11 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
 }
 
 void g16_circuit_free(g16_circuit* c) { delete c; }
+
+const char* g16_circuit_solver(const g16_circuit* c) {
+    if (!c) return "";
+    return c->plan.valid ? "gpu" : c->host_solver_reason.c_str();
+}
 
 int g16_circuit_info(const g16_circuit* c, uint64_t what[16]) {
     if (!c || !what) return G16_E_ARG;
@@ -708,6 +731,76 @@ static StageResult stage_solve(g16_circuit* c, int slot_id, size_t B, const uint
     return res;
 }
 
+// ---- stage A on the GPU: assignments -> full wire vectors in slot.d_wires (gpusolver.cu) ------------
+static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const uint8_t* assignments_be,
+                                   const uint8_t* rnd, size_t first_index) {
+    StageResult res;
+    auto failm = [&](int rc, const std::string& m) {
+        res.rc = rc;
+        res.err = m;
+        return res;
+    };
+#define G16_STAGE_CUDA(expr)                                                                  \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) return failm(G16_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+    G16_STAGE_CUDA(cudaSetDevice(c->ctx->device));
+    const Circuit& circ = c->circ;
+    const size_t nin = circ.nb_public - 1 + circ.nb_secret;
+    g16_circuit::Slot& sl = c->slots[slot_id];
+    cudaStream_t st = c->aux_stream;
+    uint8_t* h_asg = (uint8_t*)sl.h_stage;
+    uint8_t* h_rnd = h_asg + 32 * nin * c->max_batch;
+    HFr* h_chal = (HFr*)(h_rnd + 96 * c->max_batch);
+    uint32_t* h_err = (uint32_t*)((uint8_t*)h_chal + sizeof(HFr) * c->max_batch);
+    memcpy(h_asg, assignments_be, 32 * nin * B);
+    if (rnd) memcpy(h_rnd, rnd, 96 * B);
+    else
+        for (size_t k = 0; k < 3 * B; k++) {
+            HFr v;
+            if (random_fr(&v) != G16_OK) return failm(G16_E_INTERNAL, "could not read /dev/urandom");
+            v.to_be(h_rnd + 32 * k);
+        }
+    Fr* W = (Fr*)sl.d_wires.ptr;
+    uint32_t* d_err = (uint32_t*)sl.d_err.ptr;
+    G16_STAGE_CUDA(cudaMemcpyAsync(sl.d_asg_be.ptr, h_asg, 32 * nin * B, cudaMemcpyHostToDevice, st));
+    G16_STAGE_CUDA(cudaMemcpyAsync(sl.d_rnd_be.ptr, h_rnd, 96 * B, cudaMemcpyHostToDevice, st));
+    G16_STAGE_CUDA(cudaMemsetAsync(d_err, 0xff, 4 * B, st));
+    int rc = c->plan.assign((const uint8_t*)sl.d_asg_be.ptr, (const uint8_t*)sl.d_rnd_be.ptr, (uint32_t)nin, W, c->wstride, c->nw, B, st);
+    if (rc != G16_OK) return failm(rc, get_error());
+    const bool commit = c->plan.commit_level != (uint32_t)-1;
+    const uint32_t split = commit ? c->plan.commit_level + 1 : c->plan.nlevels;
+    if ((rc = c->plan.run(c->d_coeffs, c->unit_ids, W, c->wstride, c->nw, B, 0, split, d_err, st)) != G16_OK) return failm(rc, get_error());
+    sl.commits.assign(B, G1Affine::inf());
+    if (commit) {
+        rc = c->g1_aux.run(c->bCommit, W, c->wstride, c->d_map_commit, 1, B, (G1Affine*)sl.d_commit_out.ptr, st);
+        if (rc != G16_OK) return failm(rc, get_error());
+        k_fp_from_mont<<<cdiv(B * 2, 256), 256, 0, st>>>((Fp*)sl.d_commit_out.ptr, B * 2);
+        G16_STAGE_CUDA(cudaMemcpyAsync(sl.commits.data(), sl.d_commit_out.ptr, sizeof(G1Affine) * B, cudaMemcpyDeviceToHost, st));
+        G16_STAGE_CUDA(cudaStreamSynchronize(st));
+        for (size_t b = 0; b < B; b++) {
+            uint8_t msg[64];
+            g1_to_be(sl.commits[b], msg);
+            h_chal[b] = hash_to_fr(msg, 64, "bsb22-commitment");
+        }
+        G16_STAGE_CUDA(cudaMemcpyAsync(sl.d_chal.ptr, h_chal, sizeof(Fr) * B, cudaMemcpyHostToDevice, st));
+        if ((rc = c->plan.set_wire(W, c->wstride, c->plan.commit_wire, (const Fr*)sl.d_chal.ptr, B, st)) != G16_OK) return failm(rc, get_error());
+        if ((rc = c->plan.run(c->d_coeffs, c->unit_ids, W, c->wstride, c->nw, B, split, c->plan.nlevels, d_err, st)) != G16_OK)
+            return failm(rc, get_error());
+    }
+    G16_STAGE_CUDA(cudaMemcpyAsync(h_err, d_err, 4 * B, cudaMemcpyDeviceToHost, st));
+    G16_STAGE_CUDA(cudaEventRecord(sl.ready, st));
+    G16_STAGE_CUDA(cudaStreamSynchronize(st));
+    for (size_t b = 0; b < B; b++)
+        if (h_err[b] != 0xffffffffu) {
+            if (h_err[b] & 0x80000000u) return failm(G16_E_HINT, "proof " + std::to_string(first_index + b) + ": solver hint failed on the device");
+            return failm(G16_E_UNSAT, "proof " + std::to_string(first_index + b) + ": constraint #" + std::to_string(h_err[b] - 1) + " is not satisfied");
+        }
+#undef G16_STAGE_CUDA
+    return res;
+}
+
 int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, size_t n_values, const uint8_t* rnd,
                     uint8_t* proofs, uint8_t* pws, size_t pw_stride) {
     if (!c || !assignments_be || !proofs || n == 0) {
@@ -732,6 +825,9 @@ int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, siz
     auto chunk_size = [&](size_t k) { return std::min(c->max_batch, n - k * c->max_batch); };
     auto launch = [&](size_t k) {
         size_t first = k * c->max_batch;
+        if (c->plan.valid)
+            return std::async(std::launch::async, stage_solve_gpu, c, (int)(k & 1), chunk_size(k),
+                              assignments_be + first * nin * 32, rnd ? rnd + 96 * first : nullptr, first);
         return std::async(std::launch::async, stage_solve, c, (int)(k & 1), chunk_size(k), assignments_be + first * nin * 32,
                           rnd ? rnd + 96 * first : nullptr, first, true);
     };
@@ -762,7 +858,6 @@ int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, siz
             if (k + 1 < nchunks) fut.wait();   // never leave the worker running on freed state
             return rc;
         }
-        const HFr* W = (const HFr*)sl.h_wires;
         for (size_t b = 0; b < B; b++) {
             write_proof_bytes(pts[b], c->has_commitment ? &sl.commits[b] : nullptr, proofs + plen * (first + b));
             if (pws) {
@@ -771,7 +866,8 @@ int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, siz
                 for (int q = 0; q < 3; q++) {
                     o[4 * q] = hdr[q] >> 24; o[4 * q + 1] = hdr[q] >> 16; o[4 * q + 2] = hdr[q] >> 8; o[4 * q + 3] = hdr[q];
                 }
-                for (size_t i = 0; i < npub; i++) W[b * c->wstride + 1 + i].to_be(o + 12 + 32 * i);
+                for (size_t i = 0; i < npub; i++)   // public wires = the first npub assignment values, reduced mod r
+                    HFr::from_be(assignments_be + ((first + b) * nin + i) * 32).to_be(o + 12 + 32 * i);
             }
         }
     }

@@ -8,6 +8,7 @@
 
 #include "capi.cuh"
 #include "ccs.hpp"
+#include "gpusolver.cuh"
 #include "solver.hpp"
 
 namespace g16 {
@@ -28,8 +29,6 @@ struct ProvingKeyHost {
 
 int parse_pk(const uint8_t* buf, size_t len, ProvingKeyHost* out);
 
-// slots appended to every proof's wire vector on the device
-enum { X_ONE = 0, X_R = 1, X_S = 2, X_NEG_RS = 3, X_COUNT = 8 };
 
 // per-proof results of the device pipeline (canonical little-endian limbs)
 struct ProofPoints {
@@ -70,13 +69,17 @@ struct g16_circuit {
     // Two pipeline slots: while the device proves chunk k out of slot k%2, the host solves chunk
     // k+1 into the other slot (its commitment MSM runs on `aux_stream` with its own MSM scratch).
     struct Slot {
-        g16::DeviceBuf d_wires, d_commit_vals, d_commit_out;
+        g16::DeviceBuf d_wires, d_commit_vals, d_commit_out, d_asg_be, d_rnd_be, d_err, d_chal;
+        void* h_stage = nullptr;         // pinned: assignments | rnd | challenges | err
         void* h_wires = nullptr;         // pinned, max_batch * wstride Fr
         cudaEvent_t ready = nullptr;     // wires of this slot are in d_wires
         std::vector<g16::G1Affine> commits;
     } slots[2];
     cudaStream_t aux_stream = nullptr;
     g16::MsmRunner<g16::Fp> g1_aux;
+    g16::GpuSolverPlan plan;             // valid => witnesses are solved on the GPU
+    std::string host_solver_reason;
+    uint32_t* d_map_commit = nullptr;    // committed wire ids (scalar map of the commitment MSM)
     // The MSMs that only need the wires (A, B1, PoK on side[0]; B2 on side[1]) run on side streams
     // next to SpMV -> H -> K|Z on the context stream: the latency-bound tails of one MSM (scan,
     // ordering, bucket reduction) hide under another MSM's accumulation.

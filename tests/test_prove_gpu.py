@@ -113,3 +113,37 @@ def test_audit_like_circuit_proves_and_verifies(ctx):
     assert G.verify(vkd, proofs[2], pws[2])
     assert not G.verify(vkd, proofs[1], pws[0][:-1] + bytes([pws[0][-1] ^ 1]))
     circ.free()
+
+
+def test_gpu_and_host_solver_agree(ctx, golden, circuit, monkeypatch):
+    """The batched device solver (default) and the C++ host solver give the same proof bytes."""
+    assert circuit.solver == "gpu"
+    monkeypatch.setenv("G16_HOST_SOLVER", "1")
+    host = g16.Circuit(ctx, bytes.fromhex(golden["ccs"]), bytes.fromhex(golden["pk"]))
+    monkeypatch.delenv("G16_HOST_SOLVER")
+    assert host.solver != "gpu"
+    cases = golden["cases"]
+    asg = b"".join(bytes.fromhex(c["assignment"]) for c in cases)
+    rnd = b"".join(bytes.fromhex(c["rnd"]) for c in cases)
+    ph, wh = host.prove_batch(asg, len(cases), rnd)
+    pg, wg = circuit.prove_batch(asg, len(cases), rnd)
+    assert ph == pg and wh == wg
+    assert [p.hex() for p in ph] == [c["proof"] for c in cases]
+    host.free()
+
+
+def test_many_chunks_pipeline(ctx, golden, circuit):
+    """More proofs than one device batch: chunks are pipelined through two slots, order preserved."""
+    n = 2 * circuit.info["max_batch"] + 5
+    cases = [golden["cases"][i % 3] for i in range(n)]
+    asg = b"".join(bytes.fromhex(c["assignment"]) for c in cases)
+    rnd = b"".join(bytes.fromhex(c["rnd"]) for c in cases)
+    proofs, pws = circuit.prove_batch(asg, n, rnd)
+    assert [p.hex() for p in proofs] == [c["proof"] for c in cases]
+    assert [p.hex() for p in pws] == [c["pw"] for c in cases]
+    # a bad witness in the LAST chunk is reported with its global index
+    bad = bytearray(asg)
+    bad[(n - 1) * circuit.n_values * 32 + 31] ^= 1
+    with pytest.raises(g16.G16Error) as e:
+        circuit.prove_batch(bytes(bad), n, rnd)
+    assert e.value.code == 3 and "proof %d" % (n - 1) in str(e.value)
