@@ -263,8 +263,12 @@ def main():
             "config": {"workload": WORKLOAD, "proofs_per_step_per_gpu": B, "witness_solver": circ.solver,
                        "l2": "inputs larger than L2 (per-step working set > 400 MB), two input sets alternated",
                        "windows": {k: circ.info[k] for k in ("window_a", "window_b1", "window_kz", "window_b2")}},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * (wstride * 32 + circ.info["n_committed"] * 32),
-                    "d2h_bytes_per_step": B * (320 + 64), "ms_per_step": results["e2e"] / args.steps},
+            "e2e": {"value": e2e, "unit": UNIT,
+                    # GPU witness solver: only the assignments, (r,s,blinder) and the challenges go up;
+                    # proof points, commitment points and solver status come back
+                    "h2d_bytes_per_step": B * (circ.n_values * 32 + 96 + 32) if circ.solver == "gpu"
+                    else B * (wstride * 32 + circ.info["n_committed"] * 32),
+                    "d2h_bytes_per_step": B * (320 + 64 + 4), "ms_per_step": results["e2e"] / args.steps},
             "gpu_launches": results["launches"],
             "roofline": {"bound": "imad", "kernel": "k_msm_accumulate (G1+G2 bucket accumulation)",
                          "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TIMAD/s",

@@ -472,6 +472,10 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
     if (c->n >= (1u << 18)) max_batch = 1;
     else if (c->n >= (1u << 16)) max_batch = 8;
     c->max_batch = max_batch;
+    // the solver is latency-bound (one CTA per proof walks ~10^3 levels): give it 4 proving batches at a
+    // time so its latency hides behind the proving of the previous group
+    const size_t solve_batch = max_batch >= 8 ? 4 * max_batch : max_batch;
+    c->solve_batch = solve_batch;
     // ---- bases -------------------------------------------------------------------------------
     auto win = [&](size_t npts) { return msm_pick_window(npts, max_batch); };
     G16_TRY(c->bA.load(basesA.data(), basesA.size(), win(basesA.size()), 1, st));
@@ -513,17 +517,17 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
     }
     G16_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (auto& sl : c->slots) {
-        G16_TRY(sl.d_wires.ensure(sizeof(Fr) * c->wstride * max_batch));
-        G16_TRY(sl.d_commit_vals.ensure(sizeof(Fr) * (c->n_committed ? c->n_committed : 1) * max_batch));
-        G16_TRY(sl.d_commit_out.ensure(sizeof(G1Affine) * max_batch));
-        G16_CUDA(cudaMallocHost(&sl.h_wires, sizeof(Fr) * c->wstride * max_batch));
+        G16_TRY(sl.d_wires.ensure(sizeof(Fr) * c->wstride * solve_batch));
+        G16_TRY(sl.d_commit_vals.ensure(sizeof(Fr) * (c->n_committed ? c->n_committed : 1) * solve_batch));
+        G16_TRY(sl.d_commit_out.ensure(sizeof(G1Affine) * solve_batch));
+        G16_CUDA(cudaMallocHost(&sl.h_wires, sizeof(Fr) * c->wstride * solve_batch));
         G16_CUDA(cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming));
         const size_t nin = circ.nb_public - 1 + circ.nb_secret;
-        G16_TRY(sl.d_asg_be.ensure(32 * nin * max_batch));
-        G16_TRY(sl.d_rnd_be.ensure(96 * max_batch));
-        G16_TRY(sl.d_err.ensure(4 * max_batch));
-        G16_TRY(sl.d_chal.ensure(sizeof(Fr) * max_batch));
-        G16_CUDA(cudaMallocHost(&sl.h_stage, (32 * nin + 96 + sizeof(Fr) + 4) * max_batch));
+        G16_TRY(sl.d_asg_be.ensure(32 * nin * solve_batch));
+        G16_TRY(sl.d_rnd_be.ensure(96 * solve_batch));
+        G16_TRY(sl.d_err.ensure(4 * solve_batch));
+        G16_TRY(sl.d_chal.ensure(sizeof(Fr) * solve_batch));
+        G16_CUDA(cudaMallocHost(&sl.h_stage, (32 * nin + 96 + sizeof(Fr) + 4) * solve_batch));
     }
     G16_TRY(upload_vec(c->committed_wires, &c->d_map_commit, st));
     if (!getenv("G16_HOST_SOLVER")) {
@@ -751,9 +755,9 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
     g16_circuit::Slot& sl = c->slots[slot_id];
     cudaStream_t st = c->aux_stream;
     uint8_t* h_asg = (uint8_t*)sl.h_stage;
-    uint8_t* h_rnd = h_asg + 32 * nin * c->max_batch;
-    HFr* h_chal = (HFr*)(h_rnd + 96 * c->max_batch);
-    uint32_t* h_err = (uint32_t*)((uint8_t*)h_chal + sizeof(HFr) * c->max_batch);
+    uint8_t* h_rnd = h_asg + 32 * nin * c->solve_batch;
+    HFr* h_chal = (HFr*)(h_rnd + 96 * c->solve_batch);
+    uint32_t* h_err = (uint32_t*)((uint8_t*)h_chal + sizeof(HFr) * c->solve_batch);
     memcpy(h_asg, assignments_be, 32 * nin * B);
     if (rnd) memcpy(h_rnd, rnd, 96 * B);
     else
@@ -821,54 +825,59 @@ int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, siz
     G16_CUDA(cudaSetDevice(c->ctx->device));
     cudaStream_t st = c->ctx->stream;
     const size_t plen = c->has_commitment ? 388 : 324;
-    const size_t nchunks = (n + c->max_batch - 1) / c->max_batch;
-    auto chunk_size = [&](size_t k) { return std::min(c->max_batch, n - k * c->max_batch); };
-    auto launch = [&](size_t k) {
-        size_t first = k * c->max_batch;
+    // groups of solve_batch proofs are solved together (stage A); each group is proved in chunks of
+    // max_batch (stage B) while the next group is being solved
+    const size_t SB = c->solve_batch;
+    const size_t ngroups = (n + SB - 1) / SB;
+    auto group_size = [&](size_t g) { return std::min(SB, n - g * SB); };
+    auto launch = [&](size_t g) {
+        size_t first = g * SB;
         if (c->plan.valid)
-            return std::async(std::launch::async, stage_solve_gpu, c, (int)(k & 1), chunk_size(k),
+            return std::async(std::launch::async, stage_solve_gpu, c, (int)(g & 1), group_size(g),
                               assignments_be + first * nin * 32, rnd ? rnd + 96 * first : nullptr, first);
-        return std::async(std::launch::async, stage_solve, c, (int)(k & 1), chunk_size(k), assignments_be + first * nin * 32,
+        return std::async(std::launch::async, stage_solve, c, (int)(g & 1), group_size(g), assignments_be + first * nin * 32,
                           rnd ? rnd + 96 * first : nullptr, first, true);
     };
     std::future<StageResult> fut = launch(0);
     int total_launches = 0;
-    for (size_t k = 0; k < nchunks; k++) {
+    for (size_t g = 0; g < ngroups; g++) {
         StageResult sr = fut.get();
         if (sr.rc != G16_OK) {
             set_error(sr.err);
             return sr.rc;
         }
-        if (k + 1 < nchunks) fut = launch(k + 1);   // the host solves chunk k+1 while the device proves chunk k
-        const size_t B = chunk_size(k), first = k * c->max_batch;
-        g16_circuit::Slot& sl = c->slots[k & 1];
+        if (g + 1 < ngroups) fut = launch(g + 1);   // solve group g+1 while the device proves group g
+        g16_circuit::Slot& sl = c->slots[g & 1];
+        const size_t G = group_size(g);
         int rc = G16_OK;
-        std::vector<ProofPoints> pts(B);
-        do {
-            if (cudaStreamWaitEvent(st, sl.ready, 0) != cudaSuccess) { rc = G16_E_CUDA; set_error("cudaStreamWaitEvent failed"); break; }
-            if ((rc = prove_device(c, B, (const Fr*)sl.d_wires.ptr)) != G16_OK) break;
+        if (cudaStreamWaitEvent(st, sl.ready, 0) != cudaSuccess) { rc = G16_E_CUDA; set_error("cudaStreamWaitEvent failed"); }
+        for (size_t off = 0; off < G && rc == G16_OK; off += c->max_batch) {
+            const size_t B = std::min(c->max_batch, G - off), first = g * SB + off;
+            std::vector<ProofPoints> pts(B);
+            if ((rc = prove_device(c, B, (const Fr*)sl.d_wires.ptr + off * c->wstride)) != G16_OK) break;
             total_launches += c->last_launches;
             if (cudaMemcpyAsync(pts.data(), c->d_out.ptr, sizeof(ProofPoints) * B, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
                 cudaStreamSynchronize(st) != cudaSuccess) {
                 rc = G16_E_CUDA;
                 set_error(std::string("device pipeline: ") + cudaGetErrorString(cudaGetLastError()));
+                break;
             }
-        } while (0);
-        if (rc != G16_OK) {
-            if (k + 1 < nchunks) fut.wait();   // never leave the worker running on freed state
-            return rc;
-        }
-        for (size_t b = 0; b < B; b++) {
-            write_proof_bytes(pts[b], c->has_commitment ? &sl.commits[b] : nullptr, proofs + plen * (first + b));
-            if (pws) {
-                uint8_t* o = pws + pw_stride * (first + b);
-                uint32_t hdr[3] = {(uint32_t)npub, 0, (uint32_t)npub};
-                for (int q = 0; q < 3; q++) {
-                    o[4 * q] = hdr[q] >> 24; o[4 * q + 1] = hdr[q] >> 16; o[4 * q + 2] = hdr[q] >> 8; o[4 * q + 3] = hdr[q];
+            for (size_t b = 0; b < B; b++) {
+                write_proof_bytes(pts[b], c->has_commitment ? &sl.commits[off + b] : nullptr, proofs + plen * (first + b));
+                if (pws) {
+                    uint8_t* o = pws + pw_stride * (first + b);
+                    uint32_t hdr[3] = {(uint32_t)npub, 0, (uint32_t)npub};
+                    for (int q = 0; q < 3; q++) {
+                        o[4 * q] = hdr[q] >> 24; o[4 * q + 1] = hdr[q] >> 16; o[4 * q + 2] = hdr[q] >> 8; o[4 * q + 3] = hdr[q];
+                    }
+                    for (size_t i = 0; i < npub; i++)   // public wires = the first npub assignment values, reduced mod r
+                        HFr::from_be(assignments_be + ((first + b) * nin + i) * 32).to_be(o + 12 + 32 * i);
                 }
-                for (size_t i = 0; i < npub; i++)   // public wires = the first npub assignment values, reduced mod r
-                    HFr::from_be(assignments_be + ((first + b) * nin + i) * 32).to_be(o + 12 + 32 * i);
             }
+        }
+        if (rc != G16_OK) {
+            if (g + 1 < ngroups) fut.wait();   // never leave the worker running on freed state
+            return rc;
         }
     }
     c->last_launches = total_launches;
@@ -900,7 +909,7 @@ int g16_witness_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, s
         return G16_E_ARG;
     }
     for (size_t done = 0; done < n;) {
-        size_t B = std::min(c->max_batch, n - done);
+        size_t B = std::min(c->solve_batch, n - done);
         StageResult sr = stage_solve(c, 0, B, assignments_be + done * nin * 32, rnd ? rnd + 96 * done : nullptr, done, false);
         if (sr.rc != G16_OK) {
             set_error(sr.err);
