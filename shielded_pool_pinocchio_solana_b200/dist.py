@@ -33,3 +33,40 @@ def gather_proofs(local_proofs, proof_len, device="cpu"):
         b = bytes(t.cpu().numpy().tobytes())
         res += [b[i:i + proof_len] for i in range(0, len(b), proof_len)]
     return res
+
+
+# ---- one large MSM split across GPUs ------------------------------------
+def combine_partials(ctx, partials, group="g1"):
+    """Sum of the per-rank partial results (gnark raw point bytes) -- itself a tiny MSM with unit
+    scalars on the device, so no host curve arithmetic exists anywhere."""
+    one = (1).to_bytes(32, "big")
+    bases = ctx.load_bases(b"".join(partials), group, window=4)
+    try:
+        return bases.msm(one * len(partials), batch=1)
+    finally:
+        bases.free()
+
+
+def msm_sharded(ctx, points_be, scalars_be, group="g1", bases_cache=None):
+    """out = sum_i s_i P_i with the point set split into contiguous ranges, one per rank; the partial
+    sums (64 B / 128 B each) are exchanged with ONE all-gather over NCCL and added on every rank.
+    `bases_cache`: dict reused across calls so a rank's slice stays resident (a proving key is static)."""
+    size = 64 if group == "g1" else 128
+    n = len(points_be) // size
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    lo, hi = shard_range(n, rank, world)
+    key = (group, lo, hi)
+    bases = bases_cache.get(key) if bases_cache is not None else None
+    if bases is None and hi > lo:
+        bases = ctx.load_bases(points_be[lo * size:hi * size], group)
+        if bases_cache is not None:
+            bases_cache[key] = bases
+    inf = b"\x40" + b"\x00" * (size - 1)
+    partial = bases.msm(scalars_be[lo * 32:hi * 32], batch=1) if hi > lo else inf
+    if world == 1:
+        return partial
+    t = torch.frombuffer(bytearray(partial), dtype=torch.uint8).cuda()
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return combine_partials(ctx, [bytes(x.cpu().numpy().tobytes()) for x in out], group)

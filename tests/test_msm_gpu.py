@@ -71,3 +71,23 @@ def test_msm_linearity_large(ctx, n, batch):
     e = [[1 if i == j else 0 for i in range(n)]]
     assert bases.msm(enc(e), batch=1) == pts[64 * j:64 * j + 64]
     bases.free()
+
+
+@pytest.mark.parametrize("group", ["g1", "g2"])
+def test_point_range_split_and_combine(ctx, group):
+    """Multi-GPU single-MSM path (point ranges per rank + all-gather of partial sums), emulated on
+    one GPU: three unequal shards, partials combined on the device, equals the unsplit golden result."""
+    from shielded_pool_pinocchio_solana_b200.dist import combine_partials, shard_range
+    case = json.load(open(GOLDEN))[group]
+    size = 64 if group == "g1" else 128
+    pts, sc, n = bytes.fromhex(case["points"]), bytes.fromhex(case["scalars"]), case["n"]
+    partials = []
+    for r in range(3):
+        lo, hi = shard_range(n, r, 3)
+        b = ctx.load_bases(pts[lo * size:hi * size], group)
+        partials.append(b.msm(sc[lo * 32:hi * 32], batch=1))
+        b.free()
+    assert combine_partials(ctx, partials, group).hex() == case["results"][:2 * size]
+    # an all-zero shard contributes the point at infinity
+    inf = b"\x40" + b"\x00" * (size - 1)
+    assert combine_partials(ctx, partials + [inf], group).hex() == case["results"][:2 * size]
