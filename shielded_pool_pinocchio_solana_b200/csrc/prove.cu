@@ -830,11 +830,12 @@ int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, siz
     const size_t SB = c->solve_batch;
     const size_t ngroups = (n + SB - 1) / SB;
     auto group_size = [&](size_t g) { return std::min(SB, n - g * SB); };
+    const bool solve_overlap = !(getenv("G16_SOLVE_OVERLAP") && atoi(getenv("G16_SOLVE_OVERLAP")) == 0);
     auto launch = [&](size_t g) {
         size_t first = g * SB;
-        if (c->plan.valid)
-            return std::async(std::launch::async, stage_solve_gpu, c, (int)(g & 1), group_size(g),
-                              assignments_be + first * nin * 32, rnd ? rnd + 96 * first : nullptr, first);
+        if (c->plan.valid)   // G16_SOLVE_OVERLAP=0 runs the device solver between groups instead of beside them
+            return std::async(solve_overlap ? std::launch::async : std::launch::deferred, stage_solve_gpu, c, (int)(g & 1),
+                              group_size(g), assignments_be + first * nin * 32, rnd ? rnd + 96 * first : nullptr, first);
         return std::async(std::launch::async, stage_solve, c, (int)(g & 1), group_size(g), assignments_be + first * nin * 32,
                           rnd ? rnd + 96 * first : nullptr, first, true);
     };
