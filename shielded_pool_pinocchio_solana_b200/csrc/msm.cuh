@@ -337,7 +337,7 @@ __device__ XYZZ<F> small_mul(const XYZZ<F>& p, uint32_t k) {
     return r;
 }
 
-constexpr int MSM_R2_THREADS = 128;
+constexpr int MSM_R2_THREADS = 256;
 
 // reduce2: one CTA per batch element.
 //   result = sum_t acc_t + seg * sum_t t*run_t        (t = segment index)
