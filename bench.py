@@ -112,6 +112,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="proofs per step and GPU (default: circuit max_batch)")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--skip-msm", action="store_true", help="skip the standalone 2^22 G1 MSM measurement")
     args = ap.parse_args()
     rank, world, local = dist_env()
     if world != args.gpus and world != 1:
@@ -283,6 +284,36 @@ def main():
                          "launches_timed": acc_launches},
             "clocks": sampler.summary(),
         }
+        # second headline of BASELINE.json: standalone BN254 G1 MSM at 2^22 points (N=1 only)
+        if args.gpus == 1 and not args.skip_msm:
+            try:
+                n22 = 1 << 22
+                bases = ctx.load_bases(ctx.generate_points(n22, 0xB200, "g1"), "g1")
+                gen = torch.Generator(device="cuda").manual_seed(0xB201)
+                sc22 = torch.randint(-2**31, 2**31 - 1, (n22, 8), dtype=torch.int32, device="cuda", generator=gen)
+                sc22[:, 7] &= 0x0fffffff                          # canonical scalars < 2^252
+                out22 = torch.empty((1, 16), dtype=torch.int32, device="cuda")
+                for _ in range(3):
+                    bases.msm_dev(sc22.data_ptr(), 1, out22.data_ptr(), montgomery=False)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record(stream)
+                for _ in range(10):
+                    bases.msm_dev(sc22.data_ptr(), 1, out22.data_ptr(), montgomery=False)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms22 = e0.elapsed_time(e1) / 10
+                imad22 = n22 * IMAD_PER_G1_POINT / (ms22 * 1e-3) / 1e12
+                line["msm_g1_2p22"] = {"metric": "BN254 G1 MSM Mpoints/s at 2^22", "value": n22 / ms22 / 1e3, "unit": "Mpoints/s",
+                                       "ms": ms22, "window": bases.window, "achieved_timad_s": imad22,
+                                       "frac_of_imad_peak": imad22 / (imad_peak / 1e12),
+                                       "frac_of_imad_wide_roof": imad22 / (imadw_peak * 136.0 / 128.0 / 1e12),
+                                       "note": "fixed bases (window tables resident), uniform 252-bit scalars resident in HBM, whole MSM "
+                                               "(digits, sort, accumulate, reduce); work unit 23,936 IMAD per point (SURVEY.md 8d)"}
+                bases.free()
+                del sc22
+            except Exception as e:
+                line["msm_g1_2p22"] = {"error": repr(e)}
         # CPU baseline on this box's host cores, bounded sample (rank 0, N=1 only)
         if args.gpus == 1:
             try:

@@ -112,6 +112,16 @@ class SyntheticCircuit:
     def assignment_bytes(self, seed):
         return b"".join(v.to_bytes(32, "big") for v in self.assignment(seed))
 
+    def witness_gz(self, seed):
+        """The same assignment as a Noir witness file (`target/<name>.gz` of `nargo execute`):
+        gzip(bincode WitnessStack), field elements as 32 big-endian bytes."""
+        import gzip
+        vals = self.assignment(seed)
+        body = struct.pack("<Q", 1) + struct.pack("<I", 0) + struct.pack("<Q", len(vals))
+        for k, v in enumerate(vals):
+            body += struct.pack("<I", k) + struct.pack("<Q", 32) + v.to_bytes(32, "big")
+        return gzip.compress(body)
+
 
 def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=48, seed=0xA0D17,
           dens_b=5, frac_c2=0.31, n_coeffs=256):
@@ -272,7 +282,8 @@ def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=4
     body = {
         "Type": 1,
         "Public": ["1"] + ["pub_%d" % i for i in range(n_public)],
-        "Secret": ["sec_%d" % i for i in range(n_secret)],
+        # named like sunspot names ACIR witnesses, so the Noir-witness front door maps them
+        "Secret": ["__witness_%d" % (n_public + i) for i in range(n_secret)],
         "NbInternalVariables": nb_wires - first_internal,
         "NbConstraints": nrow,
         "ScalarField": "30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001",

@@ -147,3 +147,35 @@ def test_many_chunks_pipeline(ctx, golden, circuit):
     with pytest.raises(g16.G16Error) as e:
         circuit.prove_batch(bytes(bad), n, rnd)
     assert e.value.code == 3 and "proof %d" % (n - 1) in str(e.value)
+
+
+def test_noir_witness_front_door_and_cli(ctx, tmp_path):
+    """`sunspot prove <acir> <witness.gz> <ccs> <pk>` drop-in: g16_prove on a Noir-format witness and
+    the g16prove CLI with sunspot's argv write the .proof/.pw files proof.helper.ts:68-69 reads; both
+    verify, and the library call equals the assignment call under the same randomness."""
+    import subprocess
+    import groth16 as G
+    from shielded_pool_pinocchio_solana_b200 import synth
+    sc = synth.build(400, n_public=3, n_secret=12, n_committed=10, seed=11)
+    pk, vk = ctx.setup(sc.ccs, b"front-door")
+    circ = ctx.load_circuit(sc.ccs, pk)
+    rnd = bytes(range(1, 97))
+    p1, w1 = circ.prove(sc.witness_gz(5), rnd)
+    p2, w2 = circ.prove_assignment(sc.assignment_bytes(5), rnd)
+    assert (p1, w1) == (p2, w2) and len(w1) == 12 + 32 * 3
+    assert G.verify(G.read_vk(vk), p1, w1)
+    with pytest.raises(g16.G16Error) as e:
+        circ.prove(b"not a gzip stream", rnd)
+    assert e.value.code == 2
+    circ.free()
+    # CLI, same argv as sunspot (client/proof.helper.ts:64)
+    d = tmp_path / "target"
+    d.mkdir()
+    for name, data in (("c.json", b"{}"), ("c.gz", sc.witness_gz(6)), ("c.ccs", sc.ccs), ("c.pk", pk)):
+        (d / name).write_bytes(data)
+    exe = os.path.join(os.path.dirname(g16.LIB_PATH), "g16prove")
+    subprocess.check_call([exe, "prove", str(d / "c.json"), str(d / "c.gz"), str(d / "c.ccs"), str(d / "c.pk")])
+    proof, pw = (d / "c.proof").read_bytes(), (d / "c.pw").read_bytes()
+    assert len(proof) == 388 and G.verify(G.read_vk(vk), proof, pw)
+    bad = subprocess.run([exe, "prove", str(d / "c.json"), str(d / "c.ccs"), str(d / "c.ccs"), str(d / "c.pk")], capture_output=True)
+    assert bad.returncode != 0 and b"witness" in bad.stderr
