@@ -50,7 +50,7 @@ struct XYZZ {
     }
 
     // dbl-2008-s-1
-    FF_HD XYZZ dbl() const {
+    FF_NOINLINE XYZZ dbl() const {
         if (is_inf() || Y.is_zero()) return inf();
         F U = Y.dbl();
         F V = U.sqr();
@@ -90,7 +90,7 @@ struct XYZZ {
     }
 
     // this += q   (add-2008-s, 12M + 2S)
-    FF_HD void add(const XYZZ& q) {
+    FF_NOINLINE void add(const XYZZ& q) {
         if (q.is_inf()) return;
         if (is_inf()) { *this = q; return; }
         F U1 = X * q.ZZ;

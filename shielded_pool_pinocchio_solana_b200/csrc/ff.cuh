@@ -24,9 +24,12 @@
 #include <stdint.h>
 
 #if defined(__CUDACC__)
+// big curve routines used off the hot loop: real calls keep the non-hot kernels (and nvcc) small
+#define FF_NOINLINE __host__ __device__ __noinline__
 #define FF_HD __host__ __device__ __forceinline__
 #define FF_D __device__ __forceinline__
 #else
+#define FF_NOINLINE
 #define FF_HD inline
 #define FF_D inline
 #endif
