@@ -15,7 +15,7 @@
  *     handles.  A proving key is uploaded (and expanded into window tables) ONCE per
  *     g16_circuit and reused for every proof.
  *   - wire formats are gnark's: Fr = 32 B big-endian canonical; G1 = X||Y (64 B raw);
- *     G2 = X.A1||X.A0||Y.A1||Y.A0 (128 B raw); infinity = 0x40 then zeros.
+ *     G2 = X.A1||X.A0||Y.A1||Y.A0 (128 B raw); infinity = all zeros (gnark-crypto RawBytes).
  *   - "dev" entry points take DEVICE pointers (e.g. torch tensors' data_ptr()) holding
  *     little-endian 8x32-bit limbs; they only enqueue work on the context stream.
  *   - there is no CPU fallback: every compute entry point fails with G16_E_CUDA when no
@@ -151,15 +151,17 @@ int g16_prove_assignment(g16_circuit* c, const uint8_t* assignment_be, size_t n_
  * n_values * 32 B; rnd = n*96 B or NULL; proofs = n*388 B; pws = n*pw_stride B. */
 int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, size_t n_values, const uint8_t* rnd,
                     uint8_t* proofs, uint8_t* pws, size_t pw_stride);
-/* Bypass the solver: full wire vectors (nbWires * 32 B big-endian each, wire 0 = 1).  The
+/* Bypass the solver: full wire vectors (nbWires * 32 B big-endian each, wire 0 = 1); rnd as in
+ * g16_prove_batch (NULL => CSPRNG).  The
  * commitment wire must already hold the BSB22 challenge consistent with `rnd`'s blinder when a
  * valid proof is wanted; for throughput runs any vector does identical work. */
 int g16_prove_wires(g16_circuit* c, size_t n, const uint8_t* wires_be, const uint8_t* rnd, uint8_t* proofs);
 /* Device-resident throughput path: d_wires = n * nbWires Fr in Montgomery limb form already in
- * HBM (n <= max_batch, g16_circuit_info what[11]); r = s = 0.  d_proof_points receives per proof
+ * HBM (n <= max_batch, g16_circuit_info what[11]).  rnd = n*96 B host bytes (r || s || unused) or
+ * NULL => r, s from the OS CSPRNG (never zero blinding).  d_proof_points receives per proof
  * 320 bytes: Ar (G1) | Bs (G2) | Krs (G1) | PoK (G1), affine, canonical little-endian limbs.
  * Asynchronous on the context stream. */
-int g16_prove_wires_dev(g16_circuit* c, size_t n, const void* d_wires, void* d_proof_points);
+int g16_prove_wires_dev(g16_circuit* c, size_t n, const void* d_wires, const uint8_t* rnd, void* d_proof_points);
 /* Solver only (no GPU): extend an assignment to the full wire vector (nbWires * 32 B BE).
  * challenges_be: the BSB22 challenge of each commitment, supplied by the caller;
  * committed_be (optional): receives the committed values of the first commitment. */

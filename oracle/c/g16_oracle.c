@@ -184,7 +184,7 @@ static void g1_aff_from_be(g1_aff* p, const uint8_t* be) {
     fe_from_be(&p->x, be, &FP); fe_from_be(&p->y, be + 32, &FP);
 }
 static void g1_aff_to_be(uint8_t* be, const g1_aff* p) {
-    if (g1_aff_is_inf(p)) { memset(be, 0, 64); be[0] = 0x40; return; }
+    if (g1_aff_is_inf(p)) { memset(be, 0, 64); return; }
     fe_to_be(be, &p->x, &FP); fe_to_be(be + 32, &p->y, &FP);
 }
 static void g2_aff_from_be(g2_aff* p, const uint8_t* be) {
@@ -193,7 +193,7 @@ static void g2_aff_from_be(g2_aff* p, const uint8_t* be) {
     fe_from_be(&p->y.a1, be + 64, &FP); fe_from_be(&p->y.a0, be + 96, &FP);
 }
 static void g2_aff_to_be(uint8_t* be, const g2_aff* p) {
-    if (g2_aff_is_inf(p)) { memset(be, 0, 128); be[0] = 0x40; return; }
+    if (g2_aff_is_inf(p)) { memset(be, 0, 128); return; }
     fe_to_be(be, &p->x.a1, &FP); fe_to_be(be + 32, &p->x.a0, &FP);
     fe_to_be(be + 64, &p->y.a1, &FP); fe_to_be(be + 96, &p->y.a0, &FP);
 }

@@ -175,13 +175,11 @@ def solve(c, assignment, pk=None, blinder=None):
                     if side == 2:
                         val = (a * b - cc) * inv(coeff, R)
                     elif side == 0:
-                        if b == 0:
-                            raise Unsatisfied("row %d: division by zero" % c.constraint_offset[i])
-                        val = (cc * inv(b, R) - a) * inv(coeff, R)
+                        # gnark solveR1C: a zero divisor leaves the wire at 0 and only checks a*b == c
+                        # (the DivUnchecked(0, 0) = 0 convention); the row check below rejects c != 0
+                        val = 0 if b == 0 else (cc * inv(b, R) - a) * inv(coeff, R)
                     else:
-                        if a == 0:
-                            raise Unsatisfied("row %d: division by zero" % c.constraint_offset[i])
-                        val = (cc * inv(a, R) - b) * inv(coeff, R)
+                        val = 0 if a == 0 else (cc * inv(a, R) - b) * inv(coeff, R)
                     w[wid] = val % R
                 if lin(L) * lin(Rr) % R != lin(O):
                     raise Unsatisfied("constraint #%d is not satisfied" % c.constraint_offset[i])

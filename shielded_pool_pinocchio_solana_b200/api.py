@@ -195,8 +195,11 @@ class Circuit:
         check(self.ctx.lib.g16_witness_batch(self.handle, n, assignments_be, self.n_values, rnd, out))
         return out.raw
 
-    def prove_wires_dev(self, d_wires_ptr, n, d_out_ptr):
-        check(self.ctx.lib.g16_prove_wires_dev(self.handle, n, ctypes.c_void_p(d_wires_ptr), ctypes.c_void_p(d_out_ptr)))
+    def prove_wires_dev(self, d_wires_ptr, n, d_out_ptr, rnd: bytes = None):
+        """Device-resident wires in, 320-byte proof points out (device); rnd = n*96 B or None (CSPRNG)."""
+        assert rnd is None or len(rnd) == 96 * n
+        check(self.ctx.lib.g16_prove_wires_dev(self.handle, n, ctypes.c_void_p(d_wires_ptr), rnd,
+                                               ctypes.c_void_p(d_out_ptr)))
 
 
 def solve_assignment(ccs: bytes, assignment_be: bytes, nb_wires, blinder_be=None, challenges_be=b"", n_committed=0):

@@ -25,7 +25,8 @@ void limbs_to_be32(const uint32_t* limbs, uint8_t* be) {
         p[0] = limbs[i] >> 24; p[1] = limbs[i] >> 16; p[2] = limbs[i] >> 8; p[3] = limbs[i];
     }
 }
-// gnark raw G1: X||Y; infinity flagged by 0b01 in the top bits of byte 0
+// gnark raw G1: X||Y.  gnark-crypto's RawBytes writes infinity as all zeros (for bn254 the 0b01 flag
+// is the 32-byte COMPRESSED infinity); 0x40 is still accepted on input.
 void g1_from_be(const uint8_t* be, G1Affine* out) {
     if ((be[0] & 0xc0) == 0x40) { *out = G1Affine::inf(); return; }
     uint8_t tmp[32];
@@ -35,7 +36,7 @@ void g1_from_be(const uint8_t* be, G1Affine* out) {
     be32_to_limbs(be + 32, out->y.v);
 }
 void g1_to_be(const G1Affine& p, uint8_t* be) {
-    if (p.is_inf()) { memset(be, 0, 64); be[0] = 0x40; return; }
+    if (p.is_inf()) { memset(be, 0, 64); return; }
     limbs_to_be32(p.x.v, be);
     limbs_to_be32(p.y.v, be + 32);
 }
@@ -51,7 +52,7 @@ void g2_from_be(const uint8_t* be, G2Affine* out) {
     be32_to_limbs(be + 96, out->y.c0.v);
 }
 void g2_to_be(const G2Affine& p, uint8_t* be) {
-    if (p.is_inf()) { memset(be, 0, 128); be[0] = 0x40; return; }
+    if (p.is_inf()) { memset(be, 0, 128); return; }
     limbs_to_be32(p.x.c1.v, be);
     limbs_to_be32(p.x.c0.v, be + 32);
     limbs_to_be32(p.y.c1.v, be + 64);

@@ -409,6 +409,44 @@ int parse_ccs(const uint8_t* buf, size_t len, Circuit* out) {
         size_t nrows = 0;
         for (auto b : c.blueprint) nrows += (b == 1);
         if (nrows != c.nb_constraints) throw ParseError("NbConstraints does not match the R1C instruction count");
+        // every id the solvers (host and device) and the key loader will index with is range-checked
+        // once, here: hint calldata structure, wire / coefficient ids, CommitmentInfo wire ids
+        {
+            const uint64_t nw = c.nb_wires();
+            auto check_pair = [&](uint32_t cid, uint32_t wid) {
+                if (cid >= ncoef) throw ParseError("coefficient id out of range");
+                if (wid != 0xFFFFFFFFu && wid >= nw) throw ParseError("wire id out of range");
+            };
+            for (size_t i = 0; i < ninstr; i++) {
+                const uint32_t* cd = c.calldata.data() + c.start_calldata[i];
+                const uint64_t n = cd[0];
+                if (c.blueprint[i] == 1) {
+                    if (n < 4 || 4 + 2 * ((uint64_t)cd[1] + cd[2] + cd[3]) != n) throw ParseError("R1C calldata length mismatch");
+                    for (uint64_t k = 4; k < n; k += 2) check_pair(cd[k], cd[k + 1]);
+                } else if (c.blueprint[i] == 0) {
+                    if (n < 5) throw ParseError("hint calldata too short");
+                    uint64_t p = 3;
+                    for (uint32_t in = 0; in < cd[2]; in++) {
+                        if (p >= n) throw ParseError("hint calldata: input list overruns the instruction");
+                        uint64_t len_i = cd[p];
+                        if (p + 1 + 2 * len_i > n) throw ParseError("hint calldata: input expression overruns the instruction");
+                        for (uint64_t k = 0; k < len_i; k++) check_pair(cd[p + 1 + 2 * k], cd[p + 2 + 2 * k]);
+                        p += 1 + 2 * len_i;
+                    }
+                    if (p + 2 != n) throw ParseError("hint calldata length mismatch");
+                    if (cd[p] > cd[p + 1] || cd[p + 1] > nw) throw ParseError("hint output range out of bounds");
+                } else {
+                    throw ParseError("unknown blueprint id " + std::to_string(c.blueprint[i]));
+                }
+            }
+            for (auto& info : c.commitments) {
+                if (info.commitment_index >= nw) throw ParseError("CommitmentInfo.CommitmentIndex out of range");
+                for (uint32_t w : info.private_committed)
+                    if (w >= nw) throw ParseError("CommitmentInfo.PrivateCommitted wire out of range");
+                for (uint32_t w : info.public_and_commitment_committed)
+                    if (w >= nw) throw ParseError("CommitmentInfo.PublicAndCommitmentCommitted wire out of range");
+            }
+        }
         build_csr(c);
         *out = std::move(c);
         return G16_OK;

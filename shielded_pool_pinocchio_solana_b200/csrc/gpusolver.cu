@@ -151,11 +151,16 @@ k_solve_levels(const uint32_t* __restrict__ lvl_off, const uint32_t* __restrict_
             } else if (inf.x == 1) {
                 w[inf.y] = (L * Rr - O) * coeff_invs[inf.z];
             } else if (inf.x == 2) {
-                if (Rr.is_zero()) atomicMin(e, inf.w + 1);
-                else w[inf.y] = (O * Rr.inverse() - L) * coeff_invs[inf.z];
+                // zero divisor: gnark leaves the wire at 0 and only checks the row (0 == O)
+                if (Rr.is_zero()) {
+                    if (!O.is_zero()) atomicMin(e, inf.w + 1);
+                    w[inf.y] = Fr::zero();
+                } else w[inf.y] = (O * Rr.inverse() - L) * coeff_invs[inf.z];
             } else {
-                if (L.is_zero()) atomicMin(e, inf.w + 1);
-                else w[inf.y] = (O * L.inverse() - Rr) * coeff_invs[inf.z];
+                if (L.is_zero()) {
+                    if (!O.is_zero()) atomicMin(e, inf.w + 1);
+                    w[inf.y] = Fr::zero();
+                } else w[inf.y] = (O * L.inverse() - Rr) * coeff_invs[inf.z];
             }
         }
         __syncthreads();
@@ -292,6 +297,24 @@ int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not
                     auto nm = c.hint_names.find(hid);
                     *why_not = "hint without a device implementation: " + (nm == c.hint_names.end() ? std::to_string(hid) : nm->second);
                     return G16_OK;
+                }
+                if (kind == HINT_DECOMPOSE) {
+                    // the device version extracts limbs of at most 32 bits (the host one 64): larger
+                    // limb sizes, or a limb size that is not a compile-time constant, go to the host solver
+                    bool ok = nin == 3;
+                    if (ok) {
+                        size_t q = 3 + 1 + 2 * (size_t)cd[3];
+                        ok = cd[q] == 1 && cd[q + 2] == CCS_CONST_WIRE;
+                        if (ok) {
+                            uint64_t ls[4];
+                            c.coeffs[cd[q + 1]].canonical(ls);
+                            ok = !(ls[1] | ls[2] | ls[3]) && ls[0] >= 1 && ls[0] <= 32;
+                        }
+                    }
+                    if (!ok) {
+                        *why_not = "DecomposeHint with a limb size above 32 bits (host solver handles up to 64)";
+                        return G16_OK;
+                    }
                 }
                 if (kind == HINT_COUNT) {
                     // device version handles the one-column form only (what rangecheck emits)

@@ -251,8 +251,7 @@ int NttEngine::run_strided(Fr* d_data, size_t vec_stride, unsigned logn, size_t 
     const NttDomain* d;
     G16_TRY(domain(logn, st, &d));
     if (batch == 0) return G16_OK;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!attr_done) {   // per engine = per context = per device (the attribute is per device)
         int bytes = 32 << NTT_TILE_LOG;
         G16_CUDA(cudaFuncSetAttribute(k_ntt_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         G16_CUDA(cudaFuncSetAttribute(k_ntt_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));

@@ -61,6 +61,7 @@ class NttEngine {
 
    private:
     std::map<unsigned, NttDomain> domains;
+    bool attr_done = false;   // dynamic-shared-memory opt-in done on this engine's device
 };
 
 }  // namespace g16

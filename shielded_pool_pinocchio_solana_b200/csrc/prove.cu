@@ -363,13 +363,15 @@ int prove_device(g16_circuit* c, size_t B, const Fr* W) {
     return G16_OK;
 }
 
-void fill_extras(HFr* w, size_t nw, const HFr& r, const HFr& s) {
-    w[nw + X_ONE] = HFr::one();
-    w[nw + X_R] = r;
-    w[nw + X_S] = s;
-    w[nw + X_NEG_RS] = (r * s).neg();
-    for (int k = X_NEG_RS + 1; k < X_COUNT; k++) w[nw + k] = HFr::zero();
+// the X_* slots behind a wire vector: scalars of the alpha/beta/delta bases that ride along in the MSMs
+void fill_extra_slots(HFr* x, const HFr& r, const HFr& s) {
+    x[X_ONE] = HFr::one();
+    x[X_R] = r;
+    x[X_S] = s;
+    x[X_NEG_RS] = (r * s).neg();
+    for (int k = X_NEG_RS + 1; k < X_COUNT; k++) x[k] = HFr::zero();
 }
+void fill_extras(HFr* w, size_t nw, const HFr& r, const HFr& s) { fill_extra_slots(w + nw, r, s); }
 
 void write_proof_bytes(const ProofPoints& pp, const G1Affine* commitment, uint8_t* out) {
     g1_to_be(pp.ar, out);
@@ -566,19 +568,33 @@ int g16_circuit_info(const g16_circuit* c, uint64_t what[16]) {
     return G16_OK;
 }
 
-int g16_prove_wires_dev(g16_circuit* c, size_t n, const void* d_wires, void* d_proof_points) {
+int g16_prove_wires_dev(g16_circuit* c, size_t n, const void* d_wires, const uint8_t* rnd, void* d_proof_points) {
     if (!c || !d_wires || !d_proof_points || n == 0 || n > c->max_batch) {
         set_error("g16_prove_wires_dev: bad arguments (n must be 1..max_batch)");
         return G16_E_ARG;
     }
     G16_CUDA(cudaSetDevice(c->ctx->device));
     cudaStream_t st = c->ctx->stream;
-    // wires arrive without the X_* slots: lay them out with stride wstride and r = s = 0
+    // blinding scalars: injected (tests, benchmarks) or drawn from the OS CSPRNG -- never silently zero
+    std::vector<HFr> extras(X_COUNT * n);
+    for (size_t b = 0; b < n; b++) {
+        HFr r, s;
+        if (rnd) {
+            r = HFr::from_be(rnd + 96 * b);
+            s = HFr::from_be(rnd + 96 * b + 32);
+        } else {
+            G16_TRY(random_fr(&r));
+            G16_TRY(random_fr(&s));
+        }
+        fill_extra_slots(extras.data() + X_COUNT * b, r, s);
+    }
+    // wires arrive without the X_* slots: lay them out with stride wstride, then drop the extras in
     Fr* W = (Fr*)c->slots[0].d_wires.ptr;
-    G16_CUDA(cudaMemsetAsync(W, 0, sizeof(Fr) * c->wstride * n, st));
     G16_CUDA(cudaMemcpy2DAsync(W, sizeof(Fr) * c->wstride, d_wires, sizeof(Fr) * c->nw, sizeof(Fr) * c->nw, n,
                                cudaMemcpyDeviceToDevice, st));
-    k_set_one<<<cdiv(n, 128), 128, 0, st>>>(W, c->wstride, c->nw + X_ONE, (uint32_t)n);
+    // pageable source: the runtime stages it before returning, so `extras` may go out of scope
+    G16_CUDA(cudaMemcpy2DAsync(W + c->nw, sizeof(Fr) * c->wstride, extras.data(), sizeof(Fr) * X_COUNT,
+                               sizeof(Fr) * X_COUNT, n, cudaMemcpyHostToDevice, st));
     G16_TRY(prove_device(c, n, W));
     G16_CUDA(cudaMemcpyAsync(d_proof_points, c->d_out.ptr, sizeof(ProofPoints) * n, cudaMemcpyDeviceToDevice, st));
     return G16_OK;
@@ -619,13 +635,21 @@ int g16_prove_wires(g16_circuit* c, size_t n, const uint8_t* wires_be, const uin
             const uint8_t* src = wires_be + (done + b) * c->nw * 32;
             HFr* dst = w.data() + b * c->wstride;
             for (size_t i = 0; i < c->nw; i++) dst[i] = HFr::from_be(src + 32 * i);
-            HFr r = HFr::zero(), s = HFr::zero();
+            HFr r, s;
             if (rnd) {
                 r = HFr::from_be(rnd + 96 * (done + b));
                 s = HFr::from_be(rnd + 96 * (done + b) + 32);
+            } else if (random_fr(&r) != G16_OK || random_fr(&s) != G16_OK) {
+                rcs[b] = G16_E_INTERNAL;   // never fall back to r = s = 0 (a non-zero-knowledge proof)
+                return;
             }
             fill_extras(dst, c->nw, r, s);
         });
+        for (int rc : rcs)
+            if (rc != G16_OK) {
+                set_error("could not read /dev/urandom");
+                return rc;
+            }
         if (c->has_commitment) {
             // commitment point = MSM of the committed wire values over the commitment basis
             std::vector<HFr> cv(c->n_committed * B);

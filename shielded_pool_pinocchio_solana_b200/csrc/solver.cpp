@@ -179,11 +179,21 @@ int run_r1c(const Circuit& c, SolveState* st, uint32_t instr) {
     if (O.unknowns) {
         val = (L.sum * Rr.sum - O.sum) * coeff_inv(O);
     } else if (L.unknowns) {
-        if (Rr.sum.is_zero()) return fail(st, G16_E_UNSAT, "constraint #" + std::to_string(row) + ": division by zero");
-        val = (O.sum * Rr.sum.inverse() - L.sum) * coeff_inv(L);
+        // gnark solveR1C: with a zero divisor the wire stays 0 and the row is only checked (a*b == c),
+        // the DivUnchecked(0, 0) = 0 convention
+        if (Rr.sum.is_zero()) {
+            if (!O.sum.is_zero()) return fail(st, G16_E_UNSAT, "constraint #" + std::to_string(row) + " is not satisfied");
+            val = HFr::zero();
+        } else {
+            val = (O.sum * Rr.sum.inverse() - L.sum) * coeff_inv(L);
+        }
     } else {
-        if (L.sum.is_zero()) return fail(st, G16_E_UNSAT, "constraint #" + std::to_string(row) + ": division by zero");
-        val = (O.sum * L.sum.inverse() - Rr.sum) * coeff_inv(Rr);
+        if (L.sum.is_zero()) {
+            if (!O.sum.is_zero()) return fail(st, G16_E_UNSAT, "constraint #" + std::to_string(row) + " is not satisfied");
+            val = HFr::zero();
+        } else {
+            val = (O.sum * L.sum.inverse() - Rr.sum) * coeff_inv(Rr);
+        }
     }
     st->w[wid] = val;
     st->known[wid] = 1;

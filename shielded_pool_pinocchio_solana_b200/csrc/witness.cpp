@@ -42,6 +42,11 @@ static int inflate_gzip(const uint8_t* in, size_t len, std::vector<uint8_t>* out
             return G16_E_PARSE;
         }
         out->insert(out->end(), buf.data(), buf.data() + (buf.size() - zs.avail_out));
+        if (out->size() > ((size_t)1 << 30)) {   // a 2^22-wire witness stack is ~200 MB; refuse zip bombs
+            inflateEnd(&zs);
+            set_error("witness: inflated stream exceeds 1 GiB");
+            return G16_E_PARSE;
+        }
     } while (rc != Z_STREAM_END);
     inflateEnd(&zs);
     return G16_OK;

@@ -62,7 +62,7 @@ def msm_sharded(ctx, points_be, scalars_be, group="g1", bases_cache=None):
         bases = ctx.load_bases(points_be[lo * size:hi * size], group)
         if bases_cache is not None:
             bases_cache[key] = bases
-    inf = b"\x40" + b"\x00" * (size - 1)
+    inf = b"\x00" * size
     partial = bases.msm(scalars_be[lo * 32:hi * 32], batch=1) if hi > lo else inf
     if world == 1:
         return partial

@@ -124,7 +124,7 @@ class SyntheticCircuit:
 
 
 def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=48, seed=0xA0D17,
-          dens_b=5, frac_c2=0.31, n_coeffs=256):
+          dens_b=5, frac_c2=0.31, n_coeffs=256, div_zero=False):
     rng = random.Random(seed)
     assert n_public >= 2 and n_secret >= 8
     coeffs = [0, 1, 2, R - 1, R - 2] + [rng.randrange(1, R) for _ in range(n_coeffs)]
@@ -203,6 +203,13 @@ def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=4
     add_r1c([(1, S(0))], [(1, S(3))], [(1, PUB(1))])
 
     known = list(range(0, first_internal)) + [iz] + bits + limbs + mult
+    if div_zero:
+        # q * (s4 - s5) = (s6 - s7) with s4 == s5 and s6 == s7: gnark's solver leaves q = 0
+        # (DivUnchecked(0, 0) = 0) instead of failing on the zero divisor
+        dq = next_wire
+        next_wire += 1
+        add_r1c([(1, dq)], [(1, S(4)), (3, S(5))], [(1, S(6)), (3, S(7))], defines=dq)
+        known.append(dq)
     n_rows_target = n_constraints
     rows_so_far = lambda: row_count[0]
 
@@ -325,6 +332,8 @@ def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=4
         pub = [r2.randrange(R) for _ in range(n_public)]
         pub[0] = sec[0] * sec[0] % R
         pub[1] = sec[0] * sec[3] % R
+        if div_zero:
+            sec[5], sec[7] = sec[4], sec[6]
         return pub + sec
     out._assign = assign
     return out

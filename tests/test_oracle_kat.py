@@ -5,7 +5,8 @@ Nothing in the reference pins proof bytes, but these do pin forma
   * noir_circuit/target/shielded_pool_verifier.vk, audit_circuit/target/rlwe_audit.vk -- VK layout
   * client/prover-params.toml                       -- a complete public input set -> the .pw bytes
   * shielded_pool_program/src/instructions/{withdraw,submit_audit}.rs -- 388 / 172 / 76 byte framing
-Runs only where /root/reference is mounted (the build container); skipped on the GPU box.
+The artifacts are committed copies under tests/golden/ (byte-identical to the reference files; checked
+against /root/reference whenever that tree is mounted), so the suite also runs on the GPU box.
 """
 import os
 import re
@@ -17,12 +18,27 @@ import ccs
 import groth16 as G
 
 REF = "/root/reference"
-pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIXTURES = {"shielded_pool_verifier.ccs": "/noir_circuit/target/shielded_pool_verifier.ccs",
+            "shielded_pool_verifier.vk": "/noir_circuit/target/shielded_pool_verifier.vk",
+            "rlwe_audit.vk": "/audit_circuit/target/rlwe_audit.vk",
+            "audit_circuit.vk": "/audit_circuit/target/audit_circuit.vk",
+            "prover-params.toml": "/client/prover-params.toml"}
+
+
+def fixture_bytes(name):
+    return open(os.path.join(GOLD, name), "rb").read()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_committed_fixtures_are_the_reference_files():
+    for name, rel in FIXTURES.items():
+        assert fixture_bytes(name) == open(REF + rel, "rb").read(), name
 
 
 @pytest.fixture(scope="module")
 def withdraw():
-    return ccs.parse_ccs(open(REF + "/noir_circuit/target/shielded_pool_verifier.ccs", "rb").read())
+    return ccs.parse_ccs(fixture_bytes("shielded_pool_verifier.ccs"))
 
 
 def test_ccs_header_sizes_and_constants(withdraw):
@@ -99,11 +115,10 @@ def test_msm_sizes_derived_from_the_ccs(withdraw):
     assert G.domain_size(c) == 16384
 
 
-@pytest.mark.parametrize("path,nk,size", [("/noir_circuit/target/shielded_pool_verifier.vk", 7, 1296),
-                                          ("/audit_circuit/target/rlwe_audit.vk", 4, 1104),
-                                          ("/audit_circuit/target/audit_circuit.vk", 4, 1104)])
+@pytest.mark.parametrize("path,nk,size", [("shielded_pool_verifier.vk", 7, 1296), ("rlwe_audit.vk", 4, 1104),
+                                          ("audit_circuit.vk", 4, 1104)])
 def test_vk_layout_roundtrip_and_curve_membership(path, nk, size):
-    raw = open(REF + path, "rb").read()
+    raw = fixture_bytes(path)
     assert len(raw) == size
     vk = G.read_vk(raw)
     assert len(vk["K"]) == nk and len(vk["commitment_keys"]) == 1 and vk["public_and_commitment_committed"] == [[]]
@@ -117,7 +132,7 @@ def test_vk_layout_roundtrip_and_curve_membership(path, nk, size):
 def test_public_witness_bytes_from_prover_params():
     """client/prover-params.toml holds a full input set: the .pw is header + five 32-byte BE values
     (withdraw.rs:14-16, 71-90: 12-byte header, 32-byte inputs, amount in the last 8 bytes of input 3)."""
-    txt = open(REF + "/client/prover-params.toml").read()
+    txt = fixture_bytes("prover-params.toml").decode()
     val = lambda k: re.search(r"^%s\s*=\s*\"?(0x[0-9a-f]+|\d+)\"?" % k, txt, re.M).group(1)
     pub = [int(val(k), 0) for k in ("root", "nullifier", "recipient", "amount", "wa_commitment")]
     pw = G.write_public_witness(pub)
@@ -131,7 +146,7 @@ def test_cpp_parser_agrees_with_the_oracle_on_the_real_circuit():
     """The product's C++ `.ccs` parser + solver walk the same instruction stream: feeding it a witness
     that satisfies row 0..2 but not a later row reports exactly the first unsatisfied row."""
     import shielded_pool_pinocchio_solana_b200 as g16
-    real = open(REF + "/noir_circuit/target/shielded_pool_verifier.ccs", "rb").read()
+    real = fixture_bytes("shielded_pool_verifier.ccs")
     with pytest.raises(g16.G16Error) as e:
         g16.solve_assignment(real, b"\x00" * 32 * 6189, 12939, b"\x00" * 31 + b"\x01", b"\x00" * 31 + b"\x01", 490)
     assert e.value.code == 3 and "constraint #0 " in str(e.value)

@@ -1,0 +1,162 @@
+"""Byte parity AT THE BENCHMARKED SIZES: the CUDA prover against oracle/c (the C restatement of gnark's
+CPU prover, loaded into this process) on the exact configurations bench.py measures.
+
+  * audit_like (BASELINE.json configs[1]: 26,000 rows, domain 2^15, 1 commitment), a FULL device batch
+    (64 proofs, the windows / side streams / strided NTT passes of the benchmark), injected (r, s, blinder),
+    through g16_prove_batch (device solver), g16_prove_wires (host wires) and g16_prove_wires_dev
+    (device-resident wires): Ar | Bs | Krs | Commitment | PoK must equal the oracle's bytes.
+  * the same with the witness-like scalar mix of SURVEY.md 8(d) (40 % zero, 30 % one, 20 % < 2^8,
+    10 % uniform) -- hot buckets, zero/one fast paths.
+  * the reference's own withdraw circuit (tests/golden/shielded_pool_verifier.ccs, a copy of
+    /root/reference/noir_circuit/target/shielded_pool_verifier.ccs; MSM sizes 4,175 / 12,701 / 12,442 /
+    16,383 / 490): GPU setup, load, prove from seeded wire vectors (client/proof.helper.ts:64-69 proves
+    exactly this circuit), bytes = oracle/c.
+
+The oracle is the checker only; the product path never touches it.
+"""
+import hashlib
+import os
+import random
+
+import pytest
+
+import shielded_pool_pinocchio_solana_b200 as g16
+from shielded_pool_pinocchio_solana_b200 import synth
+
+pytestmark = pytest.mark.gpu
+R = synth.R
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rnd_for(i):
+    """(r, s, blinder) = SHA-256("g16b200/rnd/" || i || k) mod r  """
+    return b"".join((int.from_bytes(hashlib.sha256(b"g16b200/rnd/%d/%d" % (i, k)).digest(), "big") % R).to_bytes(32, "big")
+                    for k in range(3))
+
+
+def witness_like_wires(nw, seed):
+    """One wire vector drawn from the SURVEY 8(d) mix; wire 0 = 1."""
+    rng = random.Random(seed)
+    out = bytearray(32 * nw)
+    out[31] = 1
+    for i in range(1, nw):
+        u = rng.random()
+        if u < 0.4:
+            continue
+        v = 1 if u < 0.7 else (rng.randrange(256) if u < 0.9 else rng.randrange(R))
+        out[32 * i:32 * i + 32] = v.to_bytes(32, "big")
+    return bytes(out)
+
+
+class Oracle:
+    """oracle/c prover for one (ccs, pk): expected proof bytes from full wire vectors."""
+
+    def __init__(self, ccs_bytes, pk_bytes):
+        import ccs as occs
+        import coracle
+        import groth16 as G
+        import serialize as S
+        coracle.set_threads(os.cpu_count() or 1)
+        self.c = occs.parse_ccs(ccs_bytes)
+        pk = self.pk = G.read_pk(pk_bytes, self.c)
+        self.cc = coracle.CCircuit(self.c, pk)
+        self.coracle = coracle
+        info = self.c.commitments[0]
+        self.committed = list(info["PrivateCommitted"])
+        self.basis = b"".join(S.g1_to_bytes(p) for p in pk["commitment_keys"][0]["basis"])
+        self.nw = self.c.nb_wires
+
+    def proof(self, wires_be, rnd96):
+        """-> the 388 bytes gnark's Proof.WriteRawTo would produce for these wires and (r, s)."""
+        r, s = int.from_bytes(rnd96[:32], "big"), int.from_bytes(rnd96[32:64], "big")
+        pts = self.cc.prove_from_wires(wires_be, r, s)            # Ar | Bs | Krs | PoK
+        cv = b"".join(wires_be[32 * w:32 * w + 32] for w in self.committed)
+        commitment = self.coracle.msm(self.basis, cv, "g1")
+        return pts[:256] + b"\x00\x00\x00\x01" + commitment + pts[256:320]
+
+
+def dev_points_to_proof(raw320, commitment):
+    """g16_prove_wires_dev output (canonical LE limbs: Ar | Bs.x.c0,c1,y.c0,c1 | Krs | PoK) -> proof bytes."""
+    fe = lambda k: raw320[32 * k:32 * k + 32][::-1]
+    ar = fe(0) + fe(1)
+    bs = fe(3) + fe(2) + fe(5) + fe(4)            # gnark order X.A1 | X.A0 | Y.A1 | Y.A0
+    krs = fe(6) + fe(7)
+    pok = fe(8) + fe(9)
+    return ar + bs + krs + b"\x00\x00\x00\x01" + commitment + pok
+
+
+@pytest.fixture(scope="module")
+def audit(ctx):
+    sc = synth.audit_like()
+    pk, vk = ctx.setup(sc.ccs, b"parity-at-size")
+    circ = ctx.load_circuit(sc.ccs, pk)
+    assert circ.info["domain"] == 1 << 15 and circ.info["max_batch"] == 64
+    yield sc, circ, Oracle(sc.ccs, pk), vk
+    circ.free()
+
+
+def test_audit_like_full_batch_prove_batch_matches_oracle(audit):
+    """64 proofs from assignments (device witness solver, commitment MSM, pipelined groups) = oracle bytes."""
+    import ccs as occs
+    import groth16 as G
+    import serialize as S
+    sc, circ, orc, vk = audit
+    B = circ.info["max_batch"]
+    asg = b"".join(sc.assignment_bytes(7000 + i) for i in range(B))
+    rnd = b"".join(rnd_for(i) for i in range(B))
+    assert circ.solver == "gpu"
+    proofs, pws = circ.prove_batch(asg, B, rnd)
+    # wires from the HOST solver (independent of the device solver used above) feed the oracle prover
+    wires = circ.witness_batch(asg, B, rnd)
+    nwb = orc.nw * 32
+    # ... and the host solver itself is pinned on the big-integer oracle for one proof of the batch
+    w0, _ = G.solve(orc.c, sc.assignment(7000), orc.pk, blinder=int.from_bytes(rnd[64:96], "big"))
+    assert wires[:nwb] == b"".join(S.fr_to_bytes(x) for x in w0)
+    for i in range(B):
+        assert proofs[i] == orc.proof(wires[i * nwb:(i + 1) * nwb], rnd[96 * i:96 * i + 96]), "proof %d" % i
+    assert G.verify(G.read_vk(vk), proofs[B - 1], pws[B - 1])
+
+
+def test_audit_like_witness_mix_wires_host_and_dev(audit, ctx):
+    """Witness-like scalar mix (hot buckets: ~30 % ones, ~40 % zeros) through g16_prove_wires and
+    g16_prove_wires_dev, full batch, non-zero (r, s): bytes = oracle."""
+    import torch
+    sc, circ, orc, vk = audit
+    B = circ.info["max_batch"]
+    nw = orc.nw
+    wires = b"".join(witness_like_wires(nw, i) for i in range(B))
+    rnd = b"".join(rnd_for(100 + i) for i in range(B))
+    expect = [orc.proof(wires[i * nw * 32:(i + 1) * nw * 32], rnd[96 * i:96 * i + 96]) for i in range(B)]
+    got = circ.prove_wires(wires, B, rnd)
+    for i in range(B):
+        assert got[i] == expect[i], "prove_wires proof %d" % i
+    d_w = torch.empty((B * nw, 8), dtype=torch.int32, device="cuda")
+    ctx.fr_to_device(wires, d_w.data_ptr())
+    d_out = torch.empty((B, 80), dtype=torch.int32, device="cuda")
+    circ.prove_wires_dev(d_w.data_ptr(), B, d_out.data_ptr(), rnd)
+    ctx.sync()
+    raw = d_out.cpu().numpy().tobytes()
+    for i in range(B):
+        assert dev_points_to_proof(raw[320 * i:320 * i + 320], expect[i][260:324]) == expect[i], "prove_wires_dev proof %d" % i
+
+
+def test_real_withdraw_circuit_shape_on_gpu(ctx):
+    """The reference's withdraw .ccs: GPU `setup`, load, and proofs from seeded wire vectors equal the
+    oracle's bytes (the three sunspot/gnark-private hints are only needed to SOLVE it, not to prove it)."""
+    real = open(os.path.join(GOLD, "shielded_pool_verifier.ccs"), "rb").read()
+    pk, vk = ctx.setup(real, b"withdraw-shape")
+    circ = ctx.load_circuit(real, pk)
+    info = circ.info
+    assert (info["nb_constraints"], info["nb_wires"], info["domain"]) == (12452, 12939, 16384)
+    assert (info["n_a"], info["n_b"], info["n_k"], info["n_z"], info["n_committed"]) == (4175, 12701, 12442, 16383, 490)
+    assert len(vk) == 1296                                   # = noir_circuit/target/shielded_pool_verifier.vk
+    orc = Oracle(real, pk)
+    B = 16
+    nw = info["nb_wires"]
+    wires = b"".join(witness_like_wires(nw, 500 + i) if i % 2 else
+                     b"".join(random.Random(900 + i).randrange(R).to_bytes(32, "big") for _ in range(nw)) for i in range(B))
+    rnd = b"".join(rnd_for(200 + i) for i in range(B))
+    got = circ.prove_wires(wires, B, rnd)
+    for i in range(B):
+        assert got[i] == orc.proof(wires[i * nw * 32:(i + 1) * nw * 32], rnd[96 * i:96 * i + 96]), "proof %d" % i
+    circ.free()
