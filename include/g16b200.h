@@ -169,6 +169,15 @@ int g16_solve_assignment(const uint8_t* ccs, size_t ccs_len, const uint8_t* assi
                          const uint8_t* blinder_be, const uint8_t* challenges_be, size_t n_challenges,
                          uint8_t* wires_be, size_t wires_cap, uint8_t* committed_be, size_t committed_cap);
 
+/* ---- verification (host only, no GPU needed) ------------------------------------------------- */
+/* `sunspot verify <vk> <proof> <pw>` (noir_circuit/prove_linux.sh:87, audit_circuit/prove_audit.sh:99):
+ * gnark groth16.Verify incl. the BSB22 commitment and its Pedersen proof of knowledge.
+ * vk = VerifyingKey.WriteRawTo bytes (e.g. noir_circuit/target/shielded_pool_verifier.vk), proof =
+ * Proof.WriteRawTo (388 B), pw = public witness.  Returns G16_OK with *ok = 1 (accepted) or 0
+ * (well-formed but rejected); G16_E_PARSE when an input cannot be decoded.  Thread-safe. */
+int g16_verify(const uint8_t* vk, size_t vk_len, const uint8_t* proof, size_t proof_len, const uint8_t* pw,
+               size_t pw_len, int* ok);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,8 @@ PROTOTYPES = {
                                        ctypes.c_char_p]),
     "g16_prove_wires_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_char_p,
                                            ctypes.c_void_p]),
+    "g16_verify": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p,
+                                  ctypes.c_size_t, ctypes.POINTER(ctypes.c_int)]),
     "g16_solve_assignment": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
                                             ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p,
                                             ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]),

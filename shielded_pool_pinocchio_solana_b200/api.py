@@ -210,3 +210,12 @@ def solve_assignment(ccs: bytes, assignment_be: bytes, nb_wires, blinder_be=None
     check(lib.g16_solve_assignment(ccs, len(ccs), assignment_be, len(assignment_be) // 32, blinder_be, challenges_be,
                                    len(challenges_be) // 32, wires, len(wires), committed, n_committed * 32))
     return wires.raw, committed.raw[:n_committed * 32]
+
+
+def verify(vk: bytes, proof: bytes, pw: bytes) -> bool:
+    """`sunspot verify <vk> <proof> <pw>` (host only): True iff the proof is accepted.  Undecodable inputs
+    raise G16Error (code 2), like the non-zero exit of the reference binary."""
+    lib = _lib.load()
+    ok = ctypes.c_int(0)
+    check(lib.g16_verify(vk, len(vk), proof, len(proof), pw, len(pw), ctypes.byref(ok)))
+    return bool(ok.value)

@@ -4,7 +4,11 @@
 //        (/root/reference/client/proof.helper.ts:64, noir_circuit/prove_linux.sh:83); writes
 //        <dir-of-ccs>/<name>.proof and <name>.pw, the files proof.helper.ts:68-69 and
 //        client/generate-proof-hex.ts:18-27 read back.
-//   g16prove setup <ccs> <pk-out> <vk-out> [seed]           `sunspot setup` (prove_linux.sh:78)
+//   g16prove setup <ccs>                                    same argv as `sunspot setup` (prove_linux.sh:78):
+//        writes <name>.pk and <name>.vk next to the .ccs; fresh OS entropy (aborts if it cannot be read)
+//   g16prove setup <ccs> <pk-out> <vk-out> [seed]           explicit outputs / reproducible seed (tests)
+//   g16prove verify <vk> <proof> <pw>                       same argv as `sunspot verify` (prove_linux.sh:87):
+//        exit 0 iff the proof is accepted (host-only pairing check, no GPU needed)
 // Exit code 0 on success; non-zero with the library's message on stderr otherwise (execSync throws
 // on non-zero exit, which is the reference's only error channel).
 #include <stdio.h>
@@ -37,13 +41,29 @@ static int die(const char* what) {
 int main(int argc, char** argv) {
     if (argc < 2) {
         fprintf(stderr, "usage: g16prove prove <acir.json> <witness.gz> <ccs> <pk>\n"
-                        "       g16prove setup <ccs> <pk-out> <vk-out> [seed]\n");
+                        "       g16prove setup <ccs> [<pk-out> <vk-out> [seed]]\n"
+                        "       g16prove verify <vk> <proof> <pw>\n");
         return 2;
+    }
+    std::string cmd = argv[1];
+    if (cmd == "verify" && argc == 5) {   // host only: no CUDA context
+        std::vector<uint8_t> vk, proof, pw;
+        if (!slurp(argv[2], &vk) || !slurp(argv[3], &proof) || !slurp(argv[4], &pw)) {
+            fprintf(stderr, "g16prove: cannot read input files\n");
+            return 1;
+        }
+        int ok = 0;
+        if (g16_verify(vk.data(), vk.size(), proof.data(), proof.size(), pw.data(), pw.size(), &ok) != G16_OK) return die("verify");
+        if (!ok) {
+            fprintf(stderr, "g16prove: proof rejected\n");
+            return 1;
+        }
+        printf("proof accepted\n");
+        return 0;
     }
     int dev = getenv("G16_DEVICE") ? atoi(getenv("G16_DEVICE")) : 0;
     g16_ctx* ctx = nullptr;
     if (g16_init(&dev, 1, &ctx) != G16_OK) return die("init");
-    std::string cmd = argv[1];
     if (cmd == "prove" && argc == 6) {
         std::vector<uint8_t> acir, gz, ccs, pk;
         if (!slurp(argv[3], &gz) || !slurp(argv[4], &ccs) || !slurp(argv[5], &pk)) {
@@ -65,7 +85,7 @@ int main(int argc, char** argv) {
             return 1;
         }
         g16_circuit_free(c);
-    } else if (cmd == "setup" && (argc == 5 || argc == 6)) {
+    } else if (cmd == "setup" && (argc == 3 || argc == 5 || argc == 6)) {
         std::vector<uint8_t> ccs;
         if (!slurp(argv[2], &ccs)) {
             fprintf(stderr, "g16prove: cannot read %s\n", argv[2]);
@@ -73,10 +93,24 @@ int main(int argc, char** argv) {
         }
         std::string seed = argc == 6 ? argv[5] : "";
         if (seed.empty()) {  // fresh entropy unless a seed is given (tests / reproducible keys)
-            std::vector<uint8_t> rnd;
             std::ifstream ur("/dev/urandom", std::ios::binary);
             seed.resize(32);
             ur.read(&seed[0], 32);
+            if (!ur || ur.gcount() != 32) {   // an all-zero seed would be publicly known toxic waste
+                fprintf(stderr, "g16prove: cannot read 32 bytes of entropy from /dev/urandom\n");
+                return 1;
+            }
+        }
+        std::string pk_path, vk_path;
+        if (argc == 3) {
+            std::string base = argv[2];
+            size_t dot = base.rfind('.');
+            if (dot != std::string::npos && base.find('/', dot) == std::string::npos) base.resize(dot);
+            pk_path = base + ".pk";
+            vk_path = base + ".vk";
+        } else {
+            pk_path = argv[3];
+            vk_path = argv[4];
         }
         size_t pl = 0, vl = 0;
         if (g16_setup(ctx, ccs.data(), ccs.size(), (const uint8_t*)seed.data(), seed.size(), nullptr, &pl, nullptr, &vl) != G16_OK)
@@ -84,7 +118,7 @@ int main(int argc, char** argv) {
         std::vector<uint8_t> pk(pl), vk(vl);
         if (g16_setup(ctx, ccs.data(), ccs.size(), (const uint8_t*)seed.data(), seed.size(), pk.data(), &pl, vk.data(), &vl) != G16_OK)
             return die("setup");
-        if (!spill(argv[3], pk.data(), pl) || !spill(argv[4], vk.data(), vl)) {
+        if (!spill(pk_path, pk.data(), pl) || !spill(vk_path, vk.data(), vl)) {
             fprintf(stderr, "g16prove: cannot write key files\n");
             return 1;
         }

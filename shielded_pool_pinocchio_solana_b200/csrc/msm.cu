@@ -6,21 +6,17 @@
 namespace g16 {
 
 int msm_pick_window(size_t n, size_t batch) {
-    // cost per batch element in mixed-add equivalents: n*W(c) accumulate adds plus ~3.5 add-
-    // equivalents per bucket for the two-level reduction (full XYZZ adds cost ~1.4x a mixed add).
-    // Below ~64K bucket threads the accumulate kernel cannot fill 148 SMs, so small windows are
-    // penalised by the occupancy they leave idle.
-    const double kappa = 3.5;
-    const double want_threads = 148.0 * 1024.0;
+    // Work per batch element in modular multiplications: ~6.5 per batched-affine bucket addition
+    // (n * W of them) plus ~30 per bucket for the running-sum reduction (one mixed + one full XYZZ
+    // addition).  The tree rounds parallelise over ENTRIES, not buckets, so a small MSM no longer
+    // needs a huge window "to fill the chip" (round 1 picked c = 18 for 2^14 points).
+    (void)batch;
     int best = 8;
     double best_cost = 1e300;
-    for (int c = 8; c <= 22; c++) {
+    for (int c = 6; c <= 22; c++) {
         double W = ceil(254.0 / c);
         double nb = ldexp(1.0, c - 1);
-        double cost = (double)n * W + kappa * nb;
-        double threads = nb * (double)batch;
-        if (threads < want_threads) cost *= want_threads / threads;  // idle lanes
-        // a bucket needs a few entries on average or the warp diverges on empty buckets
+        double cost = 6.5 * (double)n * W + 30.0 * nb;
         if (cost < best_cost) {
             best_cost = cost;
             best = c;
@@ -39,8 +35,10 @@ void MsmBases<F>::release() {
 template <class F>
 int MsmBases<F>::load(const Affine<F>* host_pts, size_t n_, int c, int canonical, cudaStream_t st) {
     release();
-    if (n_ == 0 || c < 2 || c > 24) {
-        set_error("MsmBases::load: bad n or window");
+    // windows below 3 bits are refused: with 254 % c == 0 the signed-digit carry out of the top window
+    // would be lost (c = 2), and nothing is gained by such windows anyway
+    if (n_ == 0 || c < 3 || c > 24) {
+        set_error("MsmBases::load: bad n or window (3..24 bits)");
         return G16_E_ARG;
     }
     cfg = msm_config(c);
@@ -61,54 +59,42 @@ int MsmBases<F>::load(const Affine<F>* host_pts, size_t n_, int c, int canonical
     return G16_OK;
 }
 
-template <class F>
-void MsmRunner<F>::release() {
-    cudaFree(counts); cudaFree(starts); cudaFree(tile_sums); cudaFree(entries); cudaFree(order); cudaFree(size_hist);
-    order = size_hist = nullptr;
-    cudaFree(buckets); cudaFree(seg_acc); cudaFree(seg_run);
-    counts = starts = tile_sums = entries = nullptr;
-    buckets = seg_acc = seg_run = nullptr;
-    cap_buckets = cap_entries = cap_segs = cap_tiles = 0;
+int MsmScratch::ensure(size_t bytes) {
+    if (bytes <= cap) return G16_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    // grow with some slack so that slightly larger batches do not reallocate
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&ptr, want) != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        G16_CUDA(cudaMalloc(&ptr, want));
+    }
+    cap = want;
+    return G16_OK;
+}
+void MsmScratch::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
 }
 
 template <class F>
-int MsmRunner<F>::reserve(const MsmBases<F>& bases, size_t batch) {
-    size_t nbuckets = batch * bases.cfg.nb;
-    size_t nentries = batch * bases.n * bases.cfg.W;
-    size_t nsegs = nbuckets / bases.cfg.seg;
-    size_t ntiles = cdiv(nbuckets, SCAN_TILE);
-    if (nentries >= 4294967295.0 || nbuckets >= 2147483648.0) {
-        set_error("MsmRunner: batch too large for 32-bit entry offsets");
-        return G16_E_ARG;
-    }
-    if (nbuckets > cap_buckets) {
-        cudaFree(counts); cudaFree(starts); cudaFree(buckets); cudaFree(order);
-        counts = starts = order = nullptr; buckets = nullptr; cap_buckets = 0;
-        G16_CUDA(cudaMalloc(&order, 4 * nbuckets));
-        if (!size_hist) G16_CUDA(cudaMalloc(&size_hist, 4 * 2 * MSM_SIZE_BINS));
-        G16_CUDA(cudaMalloc(&counts, 4 * nbuckets));
-        G16_CUDA(cudaMalloc(&starts, 4 * nbuckets));
-        G16_CUDA(cudaMalloc(&buckets, sizeof(XYZZ<F>) * nbuckets));
-        cap_buckets = nbuckets;
-    }
-    if (nentries > cap_entries) {
-        cudaFree(entries); entries = nullptr; cap_entries = 0;
-        G16_CUDA(cudaMalloc(&entries, 4 * nentries));
-        cap_entries = nentries;
-    }
-    if (nsegs > cap_segs) {
-        cudaFree(seg_acc); cudaFree(seg_run); seg_acc = seg_run = nullptr; cap_segs = 0;
-        G16_CUDA(cudaMalloc(&seg_acc, sizeof(XYZZ<F>) * nsegs));
-        G16_CUDA(cudaMalloc(&seg_run, sizeof(XYZZ<F>) * nsegs));
-        cap_segs = nsegs;
-    }
-    if (ntiles > cap_tiles) {
-        cudaFree(tile_sums); tile_sums = nullptr; cap_tiles = 0;
-        G16_CUDA(cudaMalloc(&tile_sums, 4 * ntiles));
-        cap_tiles = ntiles;
-    }
-    return G16_OK;
+void MsmRunner<F>::release() {
+    for (auto& x : s) x.release();
 }
+
+namespace {
+constexpr int SM_COUNT = 148;   // B200
+// exclusive scan of `n` uint32 (3 launches)
+void scan_u32(const uint32_t* in, size_t n, uint32_t* tile_sums, uint32_t* out, uint32_t* out2, cudaStream_t st) {
+    const uint32_t ntiles = cdiv(n, SCAN_TILE);
+    k_scan_tile_sums<<<ntiles, SCAN_THREADS, 0, st>>>(in, n, tile_sums);
+    k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(tile_sums, ntiles);
+    k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(in, n, tile_sums, out, out2);
+}
+}  // namespace
 
 template <class F>
 int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stride, const uint32_t* d_map,
@@ -120,38 +106,149 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
         set_error("MsmRunner::run: bases not loaded");
         return G16_E_ARG;
     }
-    G16_TRY(reserve(bases, batch));
     const MsmConfig cfg = bases.cfg;
     const uint32_t n = (uint32_t)bases.n;
     const size_t nbuckets = batch * cfg.nb;
-    const uint32_t ntiles = cdiv(nbuckets, SCAN_TILE);
-    dim3 dgrid(cdiv(n, MSM_DIGIT_THREADS), (unsigned)batch);
-
-    G16_CUDA(cudaMemsetAsync(counts, 0, 4 * nbuckets, st));
-    k_msm_digits<0><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery, cfg,
-                                                         counts, nullptr);
-    k_scan_tile_sums<<<ntiles, SCAN_THREADS, 0, st>>>(counts, nbuckets, tile_sums);
-    k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(tile_sums, ntiles);
-    k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts, nbuckets, tile_sums, starts, counts);
-    k_msm_digits<1><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery, cfg,
-                                                         counts, entries);
-    // after the scatter, counts[k] (the cursor) is the END of bucket k
-    // schedule the buckets by decreasing size
-    G16_CUDA(cudaMemsetAsync(size_hist, 0, 4 * MSM_SIZE_BINS, st));
-    const unsigned ogrid = cdiv(nbuckets, MSM_ORDER_THREADS * MSM_ORDER_ITEMS);
-    k_msm_size_hist<<<ogrid, MSM_ORDER_THREADS, 0, st>>>(starts, counts, (uint32_t)nbuckets, size_hist);
-    k_msm_size_bins<<<1, MSM_SIZE_BINS, 0, st>>>(size_hist, size_hist + MSM_SIZE_BINS);
-    k_msm_order<<<ogrid, MSM_ORDER_THREADS, 0, st>>>(starts, counts, (uint32_t)nbuckets, size_hist + MSM_SIZE_BINS, order);
-    if (prof) prof->begin(sizeof(F) == sizeof(Fp) ? PROF_MSM_ACC_G1 : PROF_MSM_ACC_G2, (double)batch * n, st);
-    k_msm_accumulate<F><<<cdiv(nbuckets, 128), 128, 0, st>>>(bases.table, entries, starts, counts, order, buckets,
-                                                             (uint32_t)nbuckets);
-    if (prof) prof->end(st);
-    const uint32_t nseg = cfg.nb / cfg.seg;
+    const size_t nentries = batch * bases.n * cfg.W;   // upper bound (zero digits produce no entry)
+    if (nentries >= 4294967295.0 || nbuckets >= 2147483648.0) {
+        set_error("MsmRunner: batch too large for 32-bit entry offsets");
+        return G16_E_ARG;
+    }
+    // ---- shape of the tree -------------------------------------------------------------------
+    // R rounds halve every bucket R times; ~6 points are left for the closing XYZZ chain (a round has a
+    // fixed cost -- three launches and one inversion latency -- that a nearly empty round cannot repay).
+    // cap = 2^(R+5) - 1 bounds that chain by 32 additions for any scalar distribution.
+    const double mean = (double)bases.n * cfg.W / cfg.nb;
+    int R = (int)floor(log2(mean / 6.0) + 0.5);
+    if (R < 1) R = 1;
+    if (R > TREE_MAX_ROUNDS) R = TREE_MAX_ROUNDS;
+    const uint32_t cap = (1u << (R + 5)) - 1;
+    const size_t nvmax = nbuckets + nentries / cap + 1;
+    const size_t hot_cap = nentries / cap + 1;
+    auto items_max = [&](int r) { return (nentries >> (r + 1)) + nvmax; };   // outputs of round r
+    const bool bigk = items_max(0) >= (size_t)SM_COUNT * 4 * TREE_THREADS * 16;
+    const uint32_t K = bigk ? 16 : 4;
+    const uint32_t CH = TREE_THREADS * K;
+    constexpr int KB = 64;
+    const size_t totals_max = (size_t)cdiv(items_max(0), CH) * TREE_THREADS;
+    // ---- bucket reduction shape ----------------------------------------------------------------
+    uint32_t seg = 64;
+    while (seg > 4 && nbuckets / seg < 65536) seg >>= 1;
+    if (seg > cfg.nb) seg = cfg.nb;
+    const uint32_t nseg = cfg.nb / seg;
     const size_t nseg_total = batch * nseg;
-    k_msm_reduce1<F><<<cdiv(nseg_total, 128), 128, 0, st>>>(buckets, cfg.nb, cfg.seg, (uint32_t)nseg_total, seg_acc,
-                                                            seg_run);
-    k_msm_reduce2<F><<<(unsigned)batch, MSM_R2_THREADS, 0, st>>>(seg_acc, seg_run, nseg, cfg.seg, d_out);
-    launches = 11;
+    uint32_t parts = cdiv(nseg, 1024);
+    if (parts > 64) parts = 64;
+    const uint32_t per = cdiv(nseg, parts * MSM_R2_THREADS);
+    // ---- scratch ---------------------------------------------------------------------------------
+    const size_t ntab = 2 * VB_CLASSES + (VB_CLASSES + 1) * (1 + (size_t)R) + 8;
+    G16_TRY(s[S_COUNTS].ensure(4 * nbuckets));
+    G16_TRY(s[S_STARTS].ensure(4 * nbuckets));
+    G16_TRY(s[S_TILES].ensure(4 * ((size_t)cdiv(nbuckets + 1, SCAN_TILE) + 1)));
+    G16_TRY(s[S_ENTRIES].ensure(sizeof(Affine<F>) * nentries));
+    G16_TRY(s[S_NV].ensure(4 * (nbuckets + 1)));
+    G16_TRY(s[S_VBASE].ensure(4 * (nbuckets + 1)));
+    G16_TRY(s[S_VBSTART].ensure(4 * nvmax));
+    G16_TRY(s[S_VBSIZE].ensure(4 * nvmax));
+    G16_TRY(s[S_ORDER].ensure(4 * nvmax));
+    G16_TRY(s[S_TABLES].ensure(4 * ntab));
+    G16_TRY(s[S_HOT].ensure(4 * hot_cap));
+    G16_TRY(s[S_X0].ensure(sizeof(Affine<F>) * items_max(0)));
+    G16_TRY(s[S_X1].ensure(sizeof(Affine<F>) * items_max(1)));
+    G16_TRY(s[S_PREFIX].ensure(sizeof(F) * items_max(0)));
+    G16_TRY(s[S_TOTALS].ensure(sizeof(F) * totals_max));
+    G16_TRY(s[S_TSCRATCH].ensure(sizeof(F) * totals_max));
+    G16_TRY(s[S_RESULT].ensure(sizeof(XYZZ<F>) * nvmax));
+    G16_TRY(s[S_SEGACC].ensure(sizeof(XYZZ<F>) * nseg_total));
+    G16_TRY(s[S_SEGRUN].ensure(sizeof(XYZZ<F>) * nseg_total));
+    G16_TRY(s[S_PARTS].ensure(sizeof(XYZZ<F>) * 2 * batch * parts));
+    uint32_t* counts = (uint32_t*)s[S_COUNTS].ptr;   // doubles as the scatter cursor
+    uint32_t* starts = (uint32_t*)s[S_STARTS].ptr;
+    uint32_t* tiles = (uint32_t*)s[S_TILES].ptr;
+    Affine<F>* sorted = (Affine<F>*)s[S_ENTRIES].ptr;   // window multiples in bucket order
+    uint32_t* nv = (uint32_t*)s[S_NV].ptr;
+    uint32_t* vbase = (uint32_t*)s[S_VBASE].ptr;
+    uint32_t* vb_start = (uint32_t*)s[S_VBSTART].ptr;
+    uint32_t* vb_size = (uint32_t*)s[S_VBSIZE].ptr;
+    uint32_t* order = (uint32_t*)s[S_ORDER].ptr;
+    uint32_t* tab = (uint32_t*)s[S_TABLES].ptr;
+    uint32_t* hist = tab;                            // [VB_CLASSES]
+    uint32_t* cursor = tab + VB_CLASSES;             // [VB_CLASSES]
+    uint32_t* hot_count = tab + 2 * VB_CLASSES;      // [1] (+7 pad)
+    uint32_t* first = tab + 2 * VB_CLASSES + 8;      // [VB_CLASSES + 1]
+    uint32_t* wp = first + (VB_CLASSES + 1);         // [R][VB_CLASSES + 1]
+    uint32_t* hot_list = (uint32_t*)s[S_HOT].ptr;
+    Affine<F>* X[2] = {(Affine<F>*)s[S_X0].ptr, (Affine<F>*)s[S_X1].ptr};
+    XYZZ<F>* result_vb = (XYZZ<F>*)s[S_RESULT].ptr;
+    XYZZ<F>* seg_acc = (XYZZ<F>*)s[S_SEGACC].ptr;
+    XYZZ<F>* seg_run = (XYZZ<F>*)s[S_SEGRUN].ptr;
+    XYZZ<F>* part_out = (XYZZ<F>*)s[S_PARTS].ptr;
+
+    // ---- sort the signed digits by bucket ----------------------------------------------------------
+    dim3 dgrid(cdiv(n, MSM_DIGIT_THREADS), (unsigned)batch);
+    G16_CUDA(cudaMemsetAsync(counts, 0, 4 * nbuckets, st));
+    G16_CUDA(cudaMemsetAsync(tab, 0, 4 * (2 * VB_CLASSES + 8), st));
+    k_msm_digits<0, F><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery,
+                                                            cfg, counts, nullptr, nullptr);
+    scan_u32(counts, nbuckets, tiles, starts, counts, st);
+    k_msm_digits<1, F><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery,
+                                                            cfg, counts, bases.table, sorted);
+    // after the scatter, counts[k] (the cursor) is the END of bucket k
+    // ---- virtual buckets, size classes, schedule -------------------------------------------------------
+    k_vb_count<<<cdiv(nbuckets + 1, MSM_VB_THREADS), MSM_VB_THREADS, 0, st>>>(starts, counts, (uint32_t)nbuckets, cap, nv);
+    scan_u32(nv, nbuckets + 1, tiles, vbase, nullptr, st);
+    k_vb_fill<<<cdiv(nbuckets, MSM_VB_THREADS), MSM_VB_THREADS, 0, st>>>(starts, counts, vbase, (uint32_t)nbuckets, cap,
+                                                                         vb_start, vb_size, hist, hot_count, hot_list,
+                                                                         (uint32_t)hot_cap);
+    k_class_tables<<<1 + R, 1024, 0, st>>>(hist, first, wp, R);
+    k_vb_order<<<cdiv(nvmax, MSM_VB_THREADS), MSM_VB_THREADS, 0, st>>>(vb_size, vbase + nbuckets, first, cursor, order);
+    launches += 12;
+    // ---- tree rounds -------------------------------------------------------------------------------------
+    if (prof) prof->begin(sizeof(F) == sizeof(Fp) ? PROF_MSM_ACC_G1 : PROF_MSM_ACC_G2, (double)batch * n, st);
+    TreeArgs<F> a;
+    a.sorted = sorted;
+    a.vb_start = vb_start;
+    a.order = order;
+    a.first = first;
+    a.result_vb = result_vb;
+    a.prefix = (F*)s[S_PREFIX].ptr;
+    a.totals = (F*)s[S_TOTALS].ptr;
+    for (int r = 0; r < R; r++) {
+        a.r = r;
+        a.wp = wp + (size_t)r * (VB_CLASSES + 1);
+        a.wp_in = r ? wp + (size_t)(r - 1) * (VB_CLASSES + 1) : nullptr;
+        a.xin = r ? X[(r - 1) & 1] : nullptr;
+        a.xout = X[r & 1];
+        const size_t chunks = cdiv(items_max(r), CH);
+        const unsigned grid = (unsigned)chunks;   // one chunk per CTA: the hardware scheduler balances the tail
+        const size_t inv_chunks = cdiv(chunks * TREE_THREADS, TREE_INV_THREADS * KB);
+        const unsigned gridb = (unsigned)(inv_chunks < (size_t)SM_COUNT * 8 ? inv_chunks : SM_COUNT * 8);
+        if (bigk) k_tree_a<F, 16><<<grid, TREE_THREADS, 0, st>>>(a);
+        else k_tree_a<F, 4><<<grid, TREE_THREADS, 0, st>>>(a);
+        k_tree_b<F, KB><<<gridb, TREE_INV_THREADS, 0, st>>>(a.totals, (F*)s[S_TSCRATCH].ptr, a.wp, CH);
+        if (bigk) k_tree_c<F, 16><<<grid, TREE_THREADS, 0, st>>>(a);
+        else k_tree_c<F, 4><<<grid, TREE_THREADS, 0, st>>>(a);
+        launches += 3;
+    }
+    a.r = R;
+    a.wp_in = wp + (size_t)(R - 1) * (VB_CLASSES + 1);
+    a.xin = X[(R - 1) & 1];
+    a.wp = nullptr;
+    {
+        // buckets that still hold more than one point: at most entries / 2^R of them
+        size_t qmax = (nentries >> R) + 1;
+        if (qmax > nvmax) qmax = nvmax;
+        const size_t blocks = cdiv(qmax, 128);
+        k_tree_finish<F><<<(unsigned)(blocks < (size_t)SM_COUNT * 16 ? blocks : SM_COUNT * 16), 128, 0, st>>>(a);
+    }
+    k_vb_join<F><<<(unsigned)(hot_cap < (size_t)SM_COUNT * 2 ? hot_cap : SM_COUNT * 2), MSM_JOIN_THREADS, 0, st>>>(
+        hot_count, hot_list, (uint32_t)hot_cap, vbase, result_vb);
+    if (prof) prof->end(st);
+    // ---- bucket reduction ------------------------------------------------------------------------------------
+    k_msm_reduce1<F><<<cdiv(nseg_total, 128), 128, 0, st>>>(result_vb, vbase, seg, (uint32_t)nseg_total, seg_acc, seg_run);
+    k_msm_reduce2<F><<<(unsigned)(batch * parts), MSM_R2_THREADS, 0, st>>>(seg_acc, seg_run, nseg, parts, per, part_out);
+    k_msm_reduce3<F><<<(unsigned)batch, 32, 0, st>>>(part_out, parts, seg, d_out);
+    launches += 5;
     G16_CUDA(cudaGetLastError());
     return G16_OK;
 }
