@@ -65,7 +65,7 @@ int g16_profile_read(g16_ctx* ctx, double ms[8], double launches[8], double unit
 /* Convert `count` Fr values (32 B big-endian) to Montgomery limb form in a caller-owned device
  * buffer (count * 32 bytes), e.g. to stage inputs for the *_dev entry points. */
 int g16_fr_to_device(g16_ctx* ctx, const uint8_t* values_be, size_t count, void* d_out);
-/* Integer-pipe microbenchmark: kind 0 = IMAD (mad.lo.u32), 1 = IMAD.WIDE.U32 with carry
+/* Pipe microbenchmark: kind 0 = IMAD (mad.lo.u32), 2 = FP64 FMA, 1 = IMAD.WIDE.U32 with carry
  * (mad.lo.cc/madc.hi.cc pairs, the instruction the field multiplier is made of).
  * Writes instructions per second over the whole chip. */
 int g16_measure_imad_peak(g16_ctx* ctx, int kind, double* instr_per_s);

@@ -564,3 +564,37 @@ int oracle_prove_from_wires(const oracle_circuit* c, const uint8_t* wires_be, co
     free(w); free(wc); free(abc); free(hc); free(sA); free(sB); free(sK); free(sP);
     return 0;
 }
+
+/* ---- fixed-base batch multiplication: out[i] = [k_i] * base -------------------------------------------------
+ * The trusted setup of the oracle (oracle/py/groth16.py setup(): gnark backend/groth16/bn254/setup.go computes
+ * every key point as a multiple of the generator) and of bench.py's reference arm, which must build its own
+ * proving key without touching the product library.  8-bit windows: table[w][d] = d * 2^(8w) * base. */
+#define DEFINE_FIXED_BASE(G)                                                                                       \
+    int oracle_fixed_base_##G(const uint8_t* base_be, const uint8_t* scalars_be, size_t n, uint8_t* out_be,       \
+                              size_t pt_bytes) {                                                                  \
+        G##_aff base; G##_aff_from_be(&base, base_be);                                                            \
+        G##_aff* table = (G##_aff*)malloc(sizeof(G##_aff) * 32 * 256);                                            \
+        G##_ext cur; G##_from_aff(&cur, &base);                                                                   \
+        for (int w = 0; w < 32; w++) {                                                                            \
+            G##_ext acc; G##_set_inf(&acc);                                                                       \
+            memset(&table[w * 256], 0, sizeof(G##_aff));                                                          \
+            for (int d = 1; d < 256; d++) { G##_ext t; G##_add(&t, &acc, &cur); acc = t; G##_to_aff(&table[w * 256 + d], &acc); } \
+            G##_ext t; G##_add(&t, &acc, &cur); cur = t;                                                          \
+        }                                                                                                         \
+        uint64_t (*sc)[4] = malloc(32 * (n ? n : 1));                                                             \
+        scalars_from_be(sc, scalars_be, n);                                                                       \
+        _Pragma("omp parallel for schedule(dynamic, 64)")                                                         \
+        for (size_t i = 0; i < n; i++) {                                                                          \
+            G##_ext acc; G##_set_inf(&acc);                                                                       \
+            for (int w = 0; w < 32; w++) {                                                                        \
+                unsigned d = (unsigned)((sc[i][w >> 3] >> ((w & 7) * 8)) & 0xff);                                 \
+                if (d) G##_madd(&acc, &table[w * 256 + d], 0);                                                    \
+            }                                                                                                     \
+            G##_aff a; G##_to_aff(&a, &acc); G##_aff_to_be(out_be + pt_bytes * i, &a);                            \
+        }                                                                                                         \
+        free(sc); free(table);                                                                                    \
+        return 0;                                                                                                 \
+    }
+DEFINE_FIXED_BASE(g1)
+DEFINE_FIXED_BASE(g2)
+

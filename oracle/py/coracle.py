@@ -3,6 +3,7 @@ import ctypes
 import os
 import struct
 
+R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PATH = os.path.join(_HERE, "..", "c", "libg16oracle.so")
 _lib = None
@@ -31,6 +32,17 @@ def msm(points_be, scalars_be, group="g1"):
     fn = lib().oracle_msm_g1 if group == "g1" else lib().oracle_msm_g2
     fn(points_be, scalars_be, ctypes.c_size_t(n), out)
     return out.raw
+
+
+def fixed_base(base_be, scalars, group="g1"):
+    """[k]base for every k in `scalars` (ints) -> list of point byte strings (gnark raw encoding)."""
+    size = 64 if group == "g1" else 128
+    n = len(scalars)
+    out = ctypes.create_string_buffer(max(1, n) * size)
+    sc = b"".join((k % R_MOD).to_bytes(32, "big") for k in scalars)
+    fn = lib().oracle_fixed_base_g1 if group == "g1" else lib().oracle_fixed_base_g2
+    fn(base_be, sc, ctypes.c_size_t(n), out, ctypes.c_size_t(size))
+    return [out.raw[size * i:size * (i + 1)] for i in range(n)]
 
 
 def ntt(values_be, logn, inverse=False, coset=False):

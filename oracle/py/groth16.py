@@ -246,13 +246,40 @@ def wire_polys_at_tau(c, tau):
     return A, Bv, C
 
 
-def setup(c, seed=b"oracle"):
-    """-> (pk, vk, toxic).  Points are affine tuples / None; layout mirrors gnark's ProvingKey."""
+class _FastFixedBase:
+    """[k]G for lists of k through the C oracle (oracle/c, OpenMP) -- same results as bn254.FixedBase, used for
+    circuit sizes where the pure-Python table walk would take minutes (audit_like: ~170 K points)."""
+    def __init__(self, group):
+        import coracle
+        self.group, self.co = group, coracle
+        self.base = S.g1_to_bytes(B.G1_GEN) if group == "g1" else S.g2_to_bytes(B.G2_GEN)
+        self.dec = S.g1_from_bytes if group == "g1" else S.g2_from_bytes
+    def muls(self, ks):
+        return [self.dec(b) for b in self.co.fixed_base(self.base, list(ks), self.group)]
+    def mul(self, k):
+        return self.muls([k])[0]
+
+
+class _PyFixedBase:
+    def __init__(self, fb):
+        self.fb = fb
+    def muls(self, ks):
+        return [self.fb.mul(k) for k in ks]
+    def mul(self, k):
+        return self.fb.mul(k)
+
+
+def setup(c, seed=b"oracle", fast=False):
+    """-> (pk, vk, toxic).  Points are affine tuples / None; layout mirrors gnark's ProvingKey.
+    fast=True computes the key points with the C oracle's fixed-base multiplier."""
     tx = toxic_from_seed(seed)
     tau, alpha, beta, gamma, delta = (tx[k] for k in ("tau", "alpha", "beta", "gamma", "delta"))
     n = domain_size(c)
     A, Bv, C = wire_polys_at_tau(c, tau)
-    fb1, fb2 = B.g1_fixed_base(), B.g2_fixed_base()
+    if fast:
+        fb1, fb2 = _FastFixedBase("g1"), _FastFixedBase("g2")
+    else:
+        fb1, fb2 = _PyFixedBase(B.g1_fixed_base()), _PyFixedBase(B.g2_fixed_base())
     nw, npub = c.nb_wires, c.nb_public
     infos = c.commitments
     committed_private = [list(info["PrivateCommitted"]) for info in infos]
@@ -266,13 +293,13 @@ def setup(c, seed=b"oracle"):
         "domain": n,
         "alpha1": fb1.mul(alpha), "beta1": fb1.mul(beta), "delta1": fb1.mul(delta),
         "beta2": fb2.mul(beta), "delta2": fb2.mul(delta),
-        "A": [fb1.mul(x) for x in A if x], "B1": [fb1.mul(x) for x in Bv if x],
-        "B2": [fb2.mul(x) for x in Bv if x],
+        "A": fb1.muls([x for x in A if x]), "B1": fb1.muls([x for x in Bv if x]),
+        "B2": fb2.muls([x for x in Bv if x]),
         "infinity_a": inf_a, "infinity_b": inf_b, "nb_wires": nw,
     }
     t = [(beta * A[i] + alpha * Bv[i] + C[i]) % R for i in range(nw)]
     k_private = [i for i in range(npub, nw) if i not in in_commit and i not in commitment_wires]
-    pk["K"] = [fb1.mul(t[i] * dinv % R) for i in k_private]
+    pk["K"] = fb1.muls([t[i] * dinv % R for i in k_private])
     pk["k_wires"] = k_private
     zdt = (pow(tau, n, R) - 1) * dinv % R
     z_nat = []
@@ -282,12 +309,12 @@ def setup(c, seed=b"oracle"):
         acc = acc * tau % R
     logn = n.bit_length() - 1
     z_br = [z_nat[B.bitrev(p, logn)] for p in range(n)]
-    pk["Z"] = [fb1.mul(x) for x in z_br[:n - 1]]      # bit-reversed order, n-1 entries
+    pk["Z"] = fb1.muls(z_br[:n - 1])      # bit-reversed order, n-1 entries
     vk_wires = list(range(npub)) + commitment_wires
     vk = {
         "alpha1": pk["alpha1"], "beta1": pk["beta1"], "beta2": pk["beta2"],
         "gamma2": fb2.mul(gamma), "delta1": pk["delta1"], "delta2": pk["delta2"],
-        "K": [fb1.mul(t[i] * ginv % R) for i in vk_wires],
+        "K": fb1.muls([t[i] * ginv % R for i in vk_wires]),
         "public_and_commitment_committed": [list(info["PublicAndCommitmentCommitted"]) for info in infos],
     }
     # Pedersen keys (gnark-crypto fr/pedersen Setup): basis = gamma-scaled K of the committed wires
@@ -295,8 +322,8 @@ def setup(c, seed=b"oracle"):
     g2 = fb2.mul(tx["g2k"])
     keys = []
     for lst in committed_private:
-        basis = [fb1.mul(t[i] * ginv % R) for i in lst]
-        keys.append({"basis": basis, "basis_exp_sigma": [B.g1_mul(p, sigma) for p in basis]})
+        basis = fb1.muls([t[i] * ginv % R for i in lst])
+        keys.append({"basis": basis, "basis_exp_sigma": fb1.muls([t[i] * ginv % R * sigma % R for i in lst])})
     pk["commitment_keys"] = keys
     vk["commitment_keys"] = [{"g": g2, "g_sigma_neg": B.g2_mul(g2, (-sigma) % R)} for _ in keys]
     return pk, vk, tx

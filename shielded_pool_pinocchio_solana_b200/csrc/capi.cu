@@ -109,6 +109,26 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, uint32_t seed,
     if (s == 0x12345678u) out[0] = s;  // keep the chains alive
 }
 
+// FP64 FMA issue rate (16 independent chains per thread), for the record: DESIGN.md discusses why the
+// field multiplier stays on the integer pipe.
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, double seed, int iters) {
+    double a = seed + threadIdx.x, b = seed * 3.0 + blockIdx.x;
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = a + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int rep = 0; rep < 4; rep++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) x[i] = fma(x[i], a, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += x[i];
+    if (s == 0.12345) out[0] = s;
+}
+
 }  // namespace g16
 
 using namespace g16;
@@ -172,6 +192,7 @@ int g16_set_stream(g16_ctx* ctx, void* cuda_stream) {
 int g16_sync(g16_ctx* ctx) {
     if (!ctx) return G16_E_ARG;
     G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
     G16_CUDA(cudaStreamSynchronize(ctx->stream));
     return G16_OK;
 }
@@ -186,6 +207,7 @@ int g16_profile_enable(g16_ctx* ctx, int enable) {
 int g16_profile_read(g16_ctx* ctx, double ms[8], double launches[8], double units[8]) {
     if (!ctx || !ms || !launches || !units) return G16_E_ARG;
     G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
     ctx->prof.read(ms, launches, units);
     return G16_OK;
 }
@@ -193,6 +215,7 @@ int g16_profile_read(g16_ctx* ctx, double ms[8], double launches[8], double unit
 int g16_fr_to_device(g16_ctx* ctx, const uint8_t* values_be, size_t count, void* d_out) {
     if (!ctx || !values_be || !d_out) return G16_E_ARG;
     G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
     std::vector<Fr> tmp(count);
     for (size_t i = 0; i < count; i++) be32_to_limbs(values_be + 32 * i, tmp[i].v);
     G16_CUDA(cudaMemcpyAsync(d_out, tmp.data(), sizeof(Fr) * count, cudaMemcpyHostToDevice, ctx->stream));
@@ -204,6 +227,7 @@ int g16_fr_to_device(g16_ctx* ctx, const uint8_t* values_be, size_t count, void*
 int g16_measure_imad_peak(g16_ctx* ctx, int kind, double* instr_per_s) {
     if (!ctx || !instr_per_s) return G16_E_ARG;
     G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
     G16_TRY(ctx->scratch.ensure(64));
     const int iters = 4096;
     const int blocks = ctx->sm_count * 8;
@@ -214,7 +238,8 @@ int g16_measure_imad_peak(g16_ctx* ctx, int kind, double* instr_per_s) {
     for (int rep = 0; rep < 5; rep++) {
         G16_CUDA(cudaEventRecord(e0, ctx->stream));
         if (kind == 0) k_imad_peak<0><<<blocks, 256, 0, ctx->stream>>>((uint32_t*)ctx->scratch.ptr, 7u + rep, iters);
-        else k_imad_peak<1><<<blocks, 256, 0, ctx->stream>>>((uint32_t*)ctx->scratch.ptr, 7u + rep, iters);
+        else if (kind == 1) k_imad_peak<1><<<blocks, 256, 0, ctx->stream>>>((uint32_t*)ctx->scratch.ptr, 7u + rep, iters);
+        else k_dfma_peak<<<blocks, 256, 0, ctx->stream>>>((double*)ctx->scratch.ptr, 1.0000001 + rep, iters);
         G16_CUDA(cudaEventRecord(e1, ctx->stream));
         G16_CUDA(cudaEventSynchronize(e1));
         float ms;
@@ -224,7 +249,8 @@ int g16_measure_imad_peak(g16_ctx* ctx, int kind, double* instr_per_s) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     // kind 0: 64 IMAD per inner iteration; kind 1: 16 chains of 4 = 64 mad.lo/hi halves = 32 IMAD.WIDE
-    double per_thread = (double)iters * (kind == 0 ? 64.0 : 32.0);
+    // kind 2: 64 DFMA per inner iteration
+    double per_thread = (double)iters * (kind == 1 ? 32.0 : 64.0);
     *instr_per_s = per_thread * 256.0 * blocks / (best * 1e-3);
     return G16_OK;
 }
@@ -237,6 +263,7 @@ static int bases_load(g16_ctx* ctx, const uint8_t* points_be, size_t n, int wind
         return G16_E_ARG;
     }
     G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
     if (batch_hint == 0) batch_hint = 1;
     int c = window ? window : msm_pick_window(n, batch_hint);
     g16_bases* b = new g16_bases();
@@ -277,6 +304,7 @@ int g16_msm_dev(g16_ctx* ctx, const g16_bases* bases, const void* d_scalars, int
         return G16_E_ARG;
     }
     G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
     int rc;
     if (!bases->g2) {
         rc = ctx->g1.run(bases->b1, (const Fr*)d_scalars, bases->b1.n, nullptr, montgomery, batch, (G1Affine*)d_out,
@@ -297,6 +325,7 @@ static int msm_host(g16_ctx* ctx, const g16_bases* bases, const uint8_t* scalars
         return G16_E_ARG;
     }
     G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
     size_t n = g2 ? bases->b2.n : bases->b1.n;
     size_t ptsz = g2 ? sizeof(G2Affine) : sizeof(G1Affine);
     std::vector<Fr> sc(batch * n);
@@ -338,6 +367,7 @@ static __global__ void k_fr_from_mont(Fr* v, size_t n) {
 int g16_ntt_dev(g16_ctx* ctx, void* d_values, unsigned logn, size_t batch, int inverse, int coset) {
     if (!ctx || !d_values) return G16_E_ARG;
     G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
     const NttDomain* d;
     G16_TRY(ctx->ntt.domain(logn, ctx->stream, &d));
     ctx->ntt.launches = 0;
@@ -380,6 +410,7 @@ int g16_ntt(g16_ctx* ctx, uint8_t* values_be, unsigned logn, size_t batch, int i
         return G16_E_ARG;
     }
     G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
     size_t n = (size_t)1 << logn;
     G16_TRY(upload_fr(ctx, values_be, n * batch));
     G16_TRY(g16_ntt_dev(ctx, ctx->scalars.ptr, logn, batch, inverse, coset));
@@ -389,6 +420,7 @@ int g16_ntt(g16_ctx* ctx, uint8_t* values_be, unsigned logn, size_t batch, int i
 int g16_compute_h_dev(g16_ctx* ctx, void* d_abc, unsigned logn, size_t nproofs) {
     if (!ctx || !d_abc) return G16_E_ARG;
     G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
     ctx->ntt.launches = 0;
     int rc = ctx->ntt.compute_h((Fr*)d_abc, logn, nproofs, ctx->stream);
     ctx->last_launches = ctx->ntt.launches;
@@ -401,6 +433,7 @@ int g16_compute_h(g16_ctx* ctx, const uint8_t* abc_be, unsigned logn, size_t npr
         return G16_E_ARG;
     }
     G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
     size_t n = (size_t)1 << logn;
     G16_TRY(upload_fr(ctx, abc_be, 3 * n * nproofs));
     G16_TRY(g16_compute_h_dev(ctx, ctx->scalars.ptr, logn, nproofs));

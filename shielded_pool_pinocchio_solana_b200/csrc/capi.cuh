@@ -1,5 +1,7 @@
 // capi.cuh -- private definitions behind the opaque handles of include/g16b200.h.
 #pragma once
+#include <mutex>
+
 #include "../../include/g16b200.h"
 #include "common.cuh"
 #include "msm.cuh"
@@ -23,7 +25,14 @@ void g2_to_be(const G2Affine& p, uint8_t* be);
 
 }  // namespace g16
 
+// Every entry point that touches a context takes its (recursive) mutex: MSM / NTT scratch and the
+// streams belong to the context, so concurrent callers on one context are serialised, not corrupted
+// (SURVEY.md 8b "Threading").  For parallel host threads that must not wait on each other, use one
+// context per thread.
+#define G16_LOCK(ctxptr) std::lock_guard<std::recursive_mutex> _g16_lock((ctxptr)->mu)
+
 struct g16_ctx {
+    std::recursive_mutex mu;
     int device = 0;
     int sm_count = 0;
     cudaStream_t own_stream = nullptr;

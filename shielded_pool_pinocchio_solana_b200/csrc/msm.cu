@@ -114,23 +114,15 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
         set_error("MsmRunner: batch too large for 32-bit entry offsets");
         return G16_E_ARG;
     }
-    // ---- shape of the tree -------------------------------------------------------------------
-    // R rounds halve every bucket R times; ~6 points are left for the closing XYZZ chain (a round has a
-    // fixed cost -- three launches and one inversion latency -- that a nearly empty round cannot repay).
-    // cap = 2^(R+5) - 1 bounds that chain by 32 additions for any scalar distribution.
+    // ---- virtual buckets ----------------------------------------------------------------------
+    // A chain is at most `cap` additions long: ~2x the mean bucket size (Poisson tails stay unsplit),
+    // so only the hot buckets of a skewed scalar vector are cut, into pieces that cost what a normal
+    // bucket costs.
     const double mean = (double)bases.n * cfg.W / cfg.nb;
-    int R = (int)floor(log2(mean / 6.0) + 0.5);
-    if (R < 1) R = 1;
-    if (R > TREE_MAX_ROUNDS) R = TREE_MAX_ROUNDS;
-    const uint32_t cap = (1u << (R + 5)) - 1;
+    uint32_t cap = 63;
+    while (cap < VB_MAX_CAP && cap < 2.0 * mean) cap = 2 * cap + 1;
     const size_t nvmax = nbuckets + nentries / cap + 1;
     const size_t hot_cap = nentries / cap + 1;
-    auto items_max = [&](int r) { return (nentries >> (r + 1)) + nvmax; };   // outputs of round r
-    const bool bigk = items_max(0) >= (size_t)SM_COUNT * 4 * TREE_THREADS * 16;
-    const uint32_t K = bigk ? 16 : 4;
-    const uint32_t CH = TREE_THREADS * K;
-    constexpr int KB = 64;
-    const size_t totals_max = (size_t)cdiv(items_max(0), CH) * TREE_THREADS;
     // ---- bucket reduction shape ----------------------------------------------------------------
     uint32_t seg = 64;
     while (seg > 4 && nbuckets / seg < 65536) seg >>= 1;
@@ -141,11 +133,11 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     if (parts > 64) parts = 64;
     const uint32_t per = cdiv(nseg, parts * MSM_R2_THREADS);
     // ---- scratch ---------------------------------------------------------------------------------
-    const size_t ntab = 2 * VB_CLASSES + (VB_CLASSES + 1) * (1 + (size_t)R) + 8;
+    const size_t ntab = 2 * VB_CLASSES + (VB_CLASSES + 1) + 8;
     G16_TRY(s[S_COUNTS].ensure(4 * nbuckets));
     G16_TRY(s[S_STARTS].ensure(4 * nbuckets));
     G16_TRY(s[S_TILES].ensure(4 * ((size_t)cdiv(nbuckets + 1, SCAN_TILE) + 1)));
-    G16_TRY(s[S_ENTRIES].ensure(sizeof(Affine<F>) * nentries));
+    G16_TRY(s[S_ENTRIES].ensure(4 * nentries));
     G16_TRY(s[S_NV].ensure(4 * (nbuckets + 1)));
     G16_TRY(s[S_VBASE].ensure(4 * (nbuckets + 1)));
     G16_TRY(s[S_VBSTART].ensure(4 * nvmax));
@@ -153,11 +145,6 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     G16_TRY(s[S_ORDER].ensure(4 * nvmax));
     G16_TRY(s[S_TABLES].ensure(4 * ntab));
     G16_TRY(s[S_HOT].ensure(4 * hot_cap));
-    G16_TRY(s[S_X0].ensure(sizeof(Affine<F>) * items_max(0)));
-    G16_TRY(s[S_X1].ensure(sizeof(Affine<F>) * items_max(1)));
-    G16_TRY(s[S_PREFIX].ensure(sizeof(F) * items_max(0)));
-    G16_TRY(s[S_TOTALS].ensure(sizeof(F) * totals_max));
-    G16_TRY(s[S_TSCRATCH].ensure(sizeof(F) * totals_max));
     G16_TRY(s[S_RESULT].ensure(sizeof(XYZZ<F>) * nvmax));
     G16_TRY(s[S_SEGACC].ensure(sizeof(XYZZ<F>) * nseg_total));
     G16_TRY(s[S_SEGRUN].ensure(sizeof(XYZZ<F>) * nseg_total));
@@ -165,7 +152,7 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     uint32_t* counts = (uint32_t*)s[S_COUNTS].ptr;   // doubles as the scatter cursor
     uint32_t* starts = (uint32_t*)s[S_STARTS].ptr;
     uint32_t* tiles = (uint32_t*)s[S_TILES].ptr;
-    Affine<F>* sorted = (Affine<F>*)s[S_ENTRIES].ptr;   // window multiples in bucket order
+    uint32_t* entries = (uint32_t*)s[S_ENTRIES].ptr;
     uint32_t* nv = (uint32_t*)s[S_NV].ptr;
     uint32_t* vbase = (uint32_t*)s[S_VBASE].ptr;
     uint32_t* vb_start = (uint32_t*)s[S_VBSTART].ptr;
@@ -176,9 +163,7 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     uint32_t* cursor = tab + VB_CLASSES;             // [VB_CLASSES]
     uint32_t* hot_count = tab + 2 * VB_CLASSES;      // [1] (+7 pad)
     uint32_t* first = tab + 2 * VB_CLASSES + 8;      // [VB_CLASSES + 1]
-    uint32_t* wp = first + (VB_CLASSES + 1);         // [R][VB_CLASSES + 1]
     uint32_t* hot_list = (uint32_t*)s[S_HOT].ptr;
-    Affine<F>* X[2] = {(Affine<F>*)s[S_X0].ptr, (Affine<F>*)s[S_X1].ptr};
     XYZZ<F>* result_vb = (XYZZ<F>*)s[S_RESULT].ptr;
     XYZZ<F>* seg_acc = (XYZZ<F>*)s[S_SEGACC].ptr;
     XYZZ<F>* seg_run = (XYZZ<F>*)s[S_SEGRUN].ptr;
@@ -188,11 +173,11 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     dim3 dgrid(cdiv(n, MSM_DIGIT_THREADS), (unsigned)batch);
     G16_CUDA(cudaMemsetAsync(counts, 0, 4 * nbuckets, st));
     G16_CUDA(cudaMemsetAsync(tab, 0, 4 * (2 * VB_CLASSES + 8), st));
-    k_msm_digits<0, F><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery,
-                                                            cfg, counts, nullptr, nullptr);
+    k_msm_digits<0><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery, cfg,
+                                                         counts, nullptr);
     scan_u32(counts, nbuckets, tiles, starts, counts, st);
-    k_msm_digits<1, F><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery,
-                                                            cfg, counts, bases.table, sorted);
+    k_msm_digits<1><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery, cfg,
+                                                         counts, entries);
     // after the scatter, counts[k] (the cursor) is the END of bucket k
     // ---- virtual buckets, size classes, schedule -------------------------------------------------------
     k_vb_count<<<cdiv(nbuckets + 1, MSM_VB_THREADS), MSM_VB_THREADS, 0, st>>>(starts, counts, (uint32_t)nbuckets, cap, nv);
@@ -200,55 +185,27 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     k_vb_fill<<<cdiv(nbuckets, MSM_VB_THREADS), MSM_VB_THREADS, 0, st>>>(starts, counts, vbase, (uint32_t)nbuckets, cap,
                                                                          vb_start, vb_size, hist, hot_count, hot_list,
                                                                          (uint32_t)hot_cap);
-    k_class_tables<<<1 + R, 1024, 0, st>>>(hist, first, wp, R);
+    k_class_first<<<1, 1024, 0, st>>>(hist, first);
     k_vb_order<<<cdiv(nvmax, MSM_VB_THREADS), MSM_VB_THREADS, 0, st>>>(vb_size, vbase + nbuckets, first, cursor, order);
     launches += 12;
-    // ---- tree rounds -------------------------------------------------------------------------------------
+    // ---- bucket accumulation ---------------------------------------------------------------------------
     if (prof) prof->begin(sizeof(F) == sizeof(Fp) ? PROF_MSM_ACC_G1 : PROF_MSM_ACC_G2, (double)batch * n, st);
-    TreeArgs<F> a;
-    a.sorted = sorted;
-    a.vb_start = vb_start;
-    a.order = order;
-    a.first = first;
-    a.result_vb = result_vb;
-    a.prefix = (F*)s[S_PREFIX].ptr;
-    a.totals = (F*)s[S_TOTALS].ptr;
-    for (int r = 0; r < R; r++) {
-        a.r = r;
-        a.wp = wp + (size_t)r * (VB_CLASSES + 1);
-        a.wp_in = r ? wp + (size_t)(r - 1) * (VB_CLASSES + 1) : nullptr;
-        a.xin = r ? X[(r - 1) & 1] : nullptr;
-        a.xout = X[r & 1];
-        const size_t chunks = cdiv(items_max(r), CH);
-        const unsigned grid = (unsigned)chunks;   // one chunk per CTA: the hardware scheduler balances the tail
-        const size_t inv_chunks = cdiv(chunks * TREE_THREADS, TREE_INV_THREADS * KB);
-        const unsigned gridb = (unsigned)(inv_chunks < (size_t)SM_COUNT * 8 ? inv_chunks : SM_COUNT * 8);
-        if (bigk) k_tree_a<F, 16><<<grid, TREE_THREADS, 0, st>>>(a);
-        else k_tree_a<F, 4><<<grid, TREE_THREADS, 0, st>>>(a);
-        k_tree_b<F, KB><<<gridb, TREE_INV_THREADS, 0, st>>>(a.totals, (F*)s[S_TSCRATCH].ptr, a.wp, CH);
-        if (bigk) k_tree_c<F, 16><<<grid, TREE_THREADS, 0, st>>>(a);
-        else k_tree_c<F, 4><<<grid, TREE_THREADS, 0, st>>>(a);
-        launches += 3;
-    }
-    a.r = R;
-    a.wp_in = wp + (size_t)(R - 1) * (VB_CLASSES + 1);
-    a.xin = X[(R - 1) & 1];
-    a.wp = nullptr;
-    {
-        // buckets that still hold more than one point: at most entries / 2^R of them
-        size_t qmax = (nentries >> R) + 1;
-        if (qmax > nvmax) qmax = nvmax;
-        const size_t blocks = cdiv(qmax, 128);
-        k_tree_finish<F><<<(unsigned)(blocks < (size_t)SM_COUNT * 16 ? blocks : SM_COUNT * 16), 128, 0, st>>>(a);
-    }
-    k_vb_join<F><<<(unsigned)(hot_cap < (size_t)SM_COUNT * 2 ? hot_cap : SM_COUNT * 2), MSM_JOIN_THREADS, 0, st>>>(
-        hot_count, hot_list, (uint32_t)hot_cap, vbase, result_vb);
+    k_msm_accumulate<F><<<cdiv(nvmax, 128), 128, 0, st>>>(bases.table, entries, vb_start, vb_size, order, vbase + nbuckets,
+                                                          result_vb);
     if (prof) prof->end(st);
+    {
+        const unsigned jw = (unsigned)(cdiv(hot_cap, MSM_JOIN_THREADS / 32) < (unsigned)SM_COUNT * 8 ? cdiv(hot_cap, MSM_JOIN_THREADS / 32)
+                                                                                                 : SM_COUNT * 8);
+        const unsigned jc = (unsigned)(hot_cap / MSM_JOIN_WIDE + 1 < (size_t)SM_COUNT * 2 ? hot_cap / MSM_JOIN_WIDE + 1 : SM_COUNT * 2);
+        k_vb_join<F, false><<<jw, MSM_JOIN_THREADS, 0, st>>>(hot_count, hot_list, (uint32_t)hot_cap, vbase, result_vb);
+        k_vb_join<F, true><<<jc, MSM_JOIN_THREADS, 0, st>>>(hot_count, hot_list, (uint32_t)hot_cap, vbase, result_vb);
+    }
+    launches += 3;
     // ---- bucket reduction ------------------------------------------------------------------------------------
     k_msm_reduce1<F><<<cdiv(nseg_total, 128), 128, 0, st>>>(result_vb, vbase, seg, (uint32_t)nseg_total, seg_acc, seg_run);
     k_msm_reduce2<F><<<(unsigned)(batch * parts), MSM_R2_THREADS, 0, st>>>(seg_acc, seg_run, nseg, parts, per, part_out);
     k_msm_reduce3<F><<<(unsigned)batch, 32, 0, st>>>(part_out, parts, seg, d_out);
-    launches += 5;
+    launches += 3;
     G16_CUDA(cudaGetLastError());
     return G16_OK;
 }

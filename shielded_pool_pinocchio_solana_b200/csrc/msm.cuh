@@ -13,23 +13,23 @@
 //    combination doublings remain on the per-proof path.
 //  * A launch processes a BATCH of independent scalar vectors over the same bases (one per
 //    proof); bucket id = batch*NB + |digit|-1.
-//  * Bucket accumulation is a BATCHED-AFFINE TREE REDUCTION, not a chain per bucket:
-//      digits/histogram -> scan -> scatter (entries sorted by bucket)
-//      -> buckets cut into "virtual buckets" of at most CAP entries (hot buckets of a skewed,
-//         witness-like scalar vector are split; their partial sums are joined afterwards)
-//      -> virtual buckets ordered by size; all buckets of one size share one tree shape, so the
-//         work of a round is addressed by arithmetic on a 4096-entry class table (no per-round
-//         scans, no per-element metadata)
-//      -> R tree rounds; round r adds adjacent pairs of every bucket's current point list
-//         (affine + affine = 2M + 1S + one shared inversion).  A round is three kernels:
-//            A: denominators, per-thread prefix products      (1 modmul per addition)
-//            B: Montgomery-trick inversion of the thread totals (amortised < 0.5 modmul)
-//            C: back-substitution + the additions             (4M + 1S per addition)
-//         ~6 modmul per addition instead of the 10 of an XYZZ mixed addition, and every pair of
-//         a round is independent: a bucket holding 30 % of all entries costs the same as the
-//         same entries spread out (no thread owns a bucket).
-//      -> the <= 32 points left per virtual bucket are folded by a short XYZZ chain
-//      -> bucket reduction sum_k k*B_k by segmented running sums, multi-CTA, one normalisation.
+//  * Pipeline per launch:
+//      digits/histogram (warp-aggregated atomics) -> scan -> scatter (entry ids sorted by bucket)
+//      -> buckets cut into "virtual buckets" of at most CAP entries: the hot buckets of a skewed,
+//         witness-like scalar vector (30 % ones -> one bucket holds 30 % of all entries) become many
+//         bounded chains whose partial sums are joined afterwards
+//      -> virtual buckets ordered by decreasing size (counting sort over 4096 size classes), so the
+//         32 lanes of a warp run chains of equal length and the longest chains start first
+//      -> accumulate: thread per virtual bucket, XYZZ += affine (8M + 2S), next entry + point
+//         gathered before the add (integer-pipe bound, ~80 % of the time)
+//      -> join the pieces of split buckets -> bucket reduction sum_k k*B_k by segmented running
+//         sums (multi-CTA), one affine normalisation per result.
+//  * A batched-affine tree formulation (pairwise rounds, shared inversions: ~6 modmul per addition)
+//    was built and measured in round 2 (git history: "Batched-affine tree MSM"): bit-exact, but the
+//    operands of every addition have to be touched twice (denominator pass, addition pass), which
+//    makes the randomly gathered first round DRAM-access bound (~20 G random 64-B accesses/s on
+//    this part); end to end it lost to the chain below, which hides its single gather under 1.4 K
+//    integer instructions per addition.  See DESIGN.md 3.
 //  * Results are group elements, so they do not depend on the order in which a bucket's
 //    entries are added: the unordered atomic scatter keeps the output bit-exact.
 #pragma once
@@ -62,18 +62,17 @@ int msm_pick_window(size_t n, size_t batch);
 // ---------------------------------------------------------------------------------------------
 constexpr int MSM_DIGIT_THREADS = 256;
 
-// pass 0: count  /  pass 1: scatter the window multiples 2^(c*j) P_i themselves (sign applied) into
-// bucket order, so that every later pass streams over contiguous points.   grid = (ceil(n/256), batch)
+// pass 0: count  /  pass 1: scatter (entry = window*n + point, sign in bit 31).   grid = (ceil(n/256), batch)
 // Canonical scalar limbs are parked in shared memory ([limb][thread], conflict-free) so the
 // window loop can index them dynamically without spilling a register array to local memory.
 // Atomics are warp-aggregated (match.any on the bucket id): a witness-like scalar vector puts
 // ~30 % of its entries into bucket |digit| = 1, which would otherwise serialise on one address.
-template <int PASS, class F>
+template <int PASS>
 __global__ void __launch_bounds__(MSM_DIGIT_THREADS)
 k_msm_digits(const Fr* __restrict__ scalars, size_t scalar_stride, const Fr* __restrict__ scalars1,
              size_t scalar_stride1, const uint32_t* __restrict__ map, uint32_t n,
              int montgomery, MsmConfig cfg, uint32_t* __restrict__ counts_or_cursor,
-             const Affine<F>* __restrict__ table, Affine<F>* __restrict__ sorted) {
+             uint32_t* __restrict__ entries) {
     __shared__ uint32_t sk[8][MSM_DIGIT_THREADS];
     const uint32_t i = blockIdx.x * MSM_DIGIT_THREADS + threadIdx.x;
     const uint32_t b = blockIdx.y;
@@ -114,12 +113,7 @@ k_msm_digits(const Fr* __restrict__ scalars, size_t scalar_stride, const Fr* __r
         uint32_t pos = 0;
         if (valid && lane == leader) pos = atomicAdd(base + key, (uint32_t)__popc(peers));
         pos = __shfl_sync(0xffffffffu, pos, leader);
-        if (PASS == 1 && valid) {
-            // the table read is coalesced (consecutive i); the write lands in the bucket's run
-            Affine<F> p = table[(size_t)j * n + i];
-            if (neg) p.y = p.y.neg();
-            sorted[pos + rank] = p;
-        }
+        if (PASS == 1 && valid) entries[pos + rank] = ((uint32_t)j * n + i) | (neg << 31);
     }
 }
 
@@ -215,7 +209,6 @@ static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32
 // d = 4095 - size, so ascending d walks the sizes downwards (largest buckets first).
 constexpr int VB_CLASSES = 4096;       // sizes 0..4095
 constexpr int VB_MAX_CAP = 4095;
-constexpr int TREE_MAX_ROUNDS = 7;     // cap <= 2^(rounds+5) - 1 <= 4095
 constexpr int MSM_VB_THREADS = 256;
 
 // nv[k] = ceil(size_k / cap); nv[nbuckets] = 0 (so that the exclusive scan ends with the total)
@@ -256,31 +249,15 @@ k_vb_fill(const uint32_t* __restrict__ starts, const uint32_t* __restrict__ ends
         if (lh[i]) atomicAdd(&hist[i], lh[i]);
 }
 
-// Class tables (one CTA per table, 1024 threads x 4 classes):
-//   block 0      : first[d]  = number of virtual buckets in classes < d  (sorted position of class d)
-//   block 1 + r  : wp[r][d]  = number of round-r work items in classes < d; an item is one OUTPUT point
-//                  of the round: a bucket of size c holds m_r = ceil(c / 2^r) points before round r and
-//                  m_(r+1) after it.  Round 0 also passes single-entry buckets through.
-// Every table has VB_CLASSES + 1 entries; the last one is the total.
-__device__ __forceinline__ uint32_t tree_size_after(uint32_t c, int r) { return (c + (1u << r) - 1) >> r; }
-
-static __global__ void __launch_bounds__(1024)
-k_class_tables(const uint32_t* __restrict__ hist, uint32_t* __restrict__ first, uint32_t* __restrict__ wp, int rounds) {
+// first[d] = number of virtual buckets in classes < d (the sorted position of class d); 1024 threads x 4
+// classes; first[VB_CLASSES] = total
+static __global__ void __launch_bounds__(1024) k_class_first(const uint32_t* __restrict__ hist, uint32_t* __restrict__ first) {
     __shared__ uint32_t sh[1024];
     const int t = threadIdx.x;
-    const int r = (int)blockIdx.x - 1;
     uint32_t w[4], s = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        int d = 4 * t + k;
-        uint32_t c = VB_CLASSES - 1 - d, g = hist[d];
-        if (r < 0) {
-            w[k] = g;
-        } else {
-            uint32_t m0 = tree_size_after(c, r);
-            bool active = r == 0 ? c >= 1 : m0 >= 2;
-            w[k] = active ? g * ((m0 + 1) >> 1) : 0;
-        }
+        w[k] = hist[4 * t + k];
         s += w[k];
     }
     sh[t] = s;
@@ -292,14 +269,12 @@ k_class_tables(const uint32_t* __restrict__ hist, uint32_t* __restrict__ first, 
         __syncthreads();
     }
     uint32_t ex = sh[t] - s;
-    uint32_t* out = r < 0 ? first : wp + (size_t)r * (VB_CLASSES + 1);
-    (void)rounds;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        out[4 * t + k] = ex;
+        first[4 * t + k] = ex;
         ex += w[k];
     }
-    if (t == 1023) out[VB_CLASSES] = ex;
+    if (t == 1023) first[VB_CLASSES] = ex;
 }
 
 // order[first[d] + rank] = v : virtual buckets sorted by decreasing size (counting sort)
@@ -324,218 +299,34 @@ k_vb_order(const uint32_t* __restrict__ vb_size, const uint32_t* __restrict__ nv
 }
 
 // ---------------------------------------------------------------------------------------------
-// tree rounds
+// bucket accumulation: one thread per virtual bucket, in order of decreasing size
 // ---------------------------------------------------------------------------------------------
-constexpr int TREE_THREADS = 256;
-
 template <class F>
-struct TreeArgs {
-    const Affine<F>* sorted;     // round-0 input: points in bucket order (k_msm_digits<1>)
-    const uint32_t* vb_start;
-    const uint32_t* order;
-    const uint32_t* first;       // [VB_CLASSES + 1]
-    const uint32_t* wp_in;       // round r-1 table (input layout), unused in round 0
-    const uint32_t* wp;          // round r table
-    const Affine<F>* xin;        // input points of rounds >= 1
-    Affine<F>* xout;             // output points (buckets that still hold >= 2 points)
-    XYZZ<F>* result_vb;          // finished virtual buckets
-    F* prefix;                   // one per work item
-    F* totals;                   // one per thread-chunk
-    int r;
-};
-
-// largest d in [0, VB_CLASSES) with tab[d] <= t  (tab ascending, tab[VB_CLASSES] > t)
-__device__ __forceinline__ uint32_t class_of(const uint32_t* tab, uint32_t t) {
-    uint32_t lo = 0, hi = VB_CLASSES;   // invariant: tab[lo] <= t < tab[hi]
-#pragma unroll 1
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (tab[mid] <= t) lo = mid;
-        else hi = mid;
-    }
-    return lo;
-}
-
-struct TreeItem {
-    uint32_t in0;      // index of the first input point (in `sorted` for round 0, in `xin` later)
-    uint32_t out;      // xout index, or the virtual bucket id when to_result
-    bool has_b, to_result;
-};
-
-template <class F>
-__device__ __forceinline__ TreeItem tree_map(const TreeArgs<F>& a, const uint32_t* wp_sh, uint32_t t) {
-    TreeItem it;
-    // consecutive lanes hold consecutive t: search once per warp (lane 0), then walk forward
-    uint32_t d = __shfl_sync(0xffffffffu, class_of(wp_sh, __shfl_sync(0xffffffffu, t, 0)), 0);
-    while (wp_sh[d + 1] <= t) d++;
-    const uint32_t c = VB_CLASSES - 1 - d;
-    const uint32_t m0 = tree_size_after(c, a.r), m1 = (m0 + 1) >> 1;
-    const uint32_t local = t - wp_sh[d];
-    const uint32_t g = local / m1, j = local - g * m1;
-    const uint32_t q = a.first[d] + g;
-    it.has_b = 2 * j + 1 < m0;
-    it.to_result = m1 == 1;
-    if (a.r == 0) it.in0 = a.vb_start[a.order[q]] + 2 * j;
-    else it.in0 = a.wp_in[d] + g * m0 + 2 * j;
-    it.out = it.to_result ? a.order[q] : t;
-    return it;
-}
-
-template <class F>
-__device__ __forceinline__ Affine<F> tree_load(const TreeArgs<F>& a, uint32_t idx) {
-    return a.r == 0 ? a.sorted[idx] : a.xin[idx];
-}
-
-// what an (a, b) pair needs: 0 = no field work (a result that needs no division), 1 = chord, 2 = tangent
-template <class F>
-__device__ __forceinline__ int tree_classify(const Affine<F>& pa, const Affine<F>& pb, bool has_b, F* den) {
-    if (!has_b || pa.is_inf() || pb.is_inf()) return 0;
-    if (pa.x != pb.x) {
-        *den = pb.x - pa.x;
-        return 1;
-    }
-    if (pa.y == pb.y && !pa.y.is_zero()) {
-        *den = pa.y.dbl();
-        return 2;
-    }
-    return 0;   // P + (-P)
-}
-
-// Kernel A: per work item the denominator of its addition; per thread the running product of its
-// K denominators (prefix[t] = product of the thread's earlier ones), thread total -> totals[].
-template <class F, int K>
-__global__ void __launch_bounds__(TREE_THREADS) k_tree_a(TreeArgs<F> a) {
-    __shared__ uint32_t wp_sh[VB_CLASSES + 1];
-    for (int i = threadIdx.x; i <= VB_CLASSES; i += TREE_THREADS) wp_sh[i] = a.wp[i];
-    __syncthreads();
-    const uint32_t T = wp_sh[VB_CLASSES];
-    constexpr uint32_t CH = TREE_THREADS * K;
-    for (uint32_t chunk = blockIdx.x; (uint64_t)chunk * CH < T; chunk += gridDim.x) {
-        F run = F::one();
-#pragma unroll 1
-        for (int i = 0; i < K; i++) {
-            uint32_t t = chunk * CH + i * TREE_THREADS + threadIdx.x;
-            if (chunk * CH + i * TREE_THREADS >= T) break;          // uniform over the CTA
-            const bool live = t < T;
-            TreeItem it = tree_map(a, wp_sh, live ? t : T - 1);     // whole warps map together (shuffles inside)
-            if (!live) continue;
-            a.prefix[t] = run;
-            if (!it.has_b) continue;
-            Affine<F> pa = tree_load(a, it.in0), pb = tree_load(a, it.in0 + 1);
-            F den;
-            if (tree_classify(pa, pb, true, &den)) run = run * den;
+__global__ void __launch_bounds__(128)
+k_msm_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ entries,
+                 const uint32_t* __restrict__ vb_start, const uint32_t* __restrict__ vb_size,
+                 const uint32_t* __restrict__ order, const uint32_t* __restrict__ nv_total,
+                 XYZZ<F>* __restrict__ result_vb) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= *nv_total) return;
+    const uint32_t v = order[q];
+    const uint32_t s = vb_start[v], e = s + vb_size[v];   // size >= 1
+    XYZZ<F> acc = XYZZ<F>::inf();
+    uint32_t en = entries[s];
+    Affine<F> p = table[en & 0x7fffffffu];
+    for (uint32_t it = s; it < e; it++) {
+        uint32_t en_next = 0;
+        Affine<F> pn = p;
+        if (it + 1 < e) {  // issue the next gather before the ~1.4k-IMAD add
+            en_next = entries[it + 1];
+            pn = table[en_next & 0x7fffffffu];
         }
-        a.totals[(size_t)chunk * TREE_THREADS + threadIdx.x] = run;
+        if (en >> 31) p.y = p.y.neg();
+        acc.madd(p);
+        en = en_next;
+        p = pn;
     }
-}
-
-// Kernel B: in-place inversion of `count` field elements, KB per thread with Montgomery's trick
-// (one true inversion per KB elements).  Zeros cannot occur (denominators are non-zero).
-constexpr int TREE_INV_THREADS = 128;
-template <class F, int KB>
-__global__ void __launch_bounds__(TREE_INV_THREADS)
-k_tree_b(F* __restrict__ totals, F* __restrict__ scratch, const uint32_t* __restrict__ wp, uint32_t items_per_chunk) {
-    const uint32_t T = wp[VB_CLASSES];
-    const uint32_t nchunks = (T + items_per_chunk - 1) / items_per_chunk;
-    const uint64_t count = (uint64_t)nchunks * TREE_THREADS;
-    constexpr uint32_t CH = TREE_INV_THREADS * KB;
-    for (uint64_t base = (uint64_t)blockIdx.x * CH; base < count; base += (uint64_t)gridDim.x * CH) {
-        F run = F::one();
-        int used = 0;
-#pragma unroll 1
-        for (int i = 0; i < KB; i++) {
-            uint64_t idx = base + (uint64_t)i * TREE_INV_THREADS + threadIdx.x;
-            if (idx >= count) break;
-            scratch[idx] = run;
-            run = run * totals[idx];
-            used = i + 1;
-        }
-        if (used == 0) continue;
-        F inv = run.inverse();
-#pragma unroll 1
-        for (int i = used - 1; i >= 0; i--) {
-            uint64_t idx = base + (uint64_t)i * TREE_INV_THREADS + threadIdx.x;
-            F x = totals[idx];
-            totals[idx] = inv * scratch[idx];
-            inv = inv * x;
-        }
-    }
-}
-
-// Kernel C: walks the thread's items backwards, peels 1/den off the inverted total and adds.
-template <class F, int K>
-__global__ void __launch_bounds__(TREE_THREADS) k_tree_c(TreeArgs<F> a) {
-    __shared__ uint32_t wp_sh[VB_CLASSES + 1];
-    for (int i = threadIdx.x; i <= VB_CLASSES; i += TREE_THREADS) wp_sh[i] = a.wp[i];
-    __syncthreads();
-    const uint32_t T = wp_sh[VB_CLASSES];
-    constexpr uint32_t CH = TREE_THREADS * K;
-    for (uint32_t chunk = blockIdx.x; (uint64_t)chunk * CH < T; chunk += gridDim.x) {
-        F inv = a.totals[(size_t)chunk * TREE_THREADS + threadIdx.x];
-        int last = -1;
-        {
-            uint64_t first_t = (uint64_t)chunk * CH + threadIdx.x;
-            if (first_t < T) last = (int)min((uint64_t)(K - 1), (T - 1 - first_t) / TREE_THREADS);
-        }
-#pragma unroll 1
-        for (int i = K - 1; i >= 0; i--) {
-            uint32_t t = chunk * CH + i * TREE_THREADS + threadIdx.x;
-            if (chunk * CH + i * TREE_THREADS >= T) continue;       // uniform over the CTA
-            TreeItem it = tree_map(a, wp_sh, i <= last ? t : T - 1);
-            if (i > last) continue;
-            Affine<F> pa = tree_load(a, it.in0), pb = pa;
-            if (it.has_b) pb = tree_load(a, it.in0 + 1);
-            F den;
-            int kind = tree_classify(pa, pb, it.has_b, &den);
-            Affine<F> o;
-            if (kind == 0) {
-                if (!it.has_b || pb.is_inf()) o = pa;
-                else if (pa.is_inf()) o = pb;
-                else o = Affine<F>::inf();
-            } else {
-                F dinv = inv * a.prefix[t];
-                inv = inv * den;
-                F num;
-                if (kind == 1) {
-                    num = pb.y - pa.y;
-                } else {
-                    F xx = pa.x.sqr();
-                    num = xx.dbl() + xx;
-                }
-                F lam = num * dinv;
-                o.x = lam.sqr() - pa.x - pb.x;
-                o.y = lam * (pa.x - o.x) - pa.y;
-            }
-            if (it.to_result) a.result_vb[it.out] = XYZZ<F>::from_affine(o);
-            else a.xout[it.out] = o;
-        }
-    }
-}
-
-// After the last tree round every virtual bucket of size > 2^R still holds m_R <= 32 points (R = 0:
-// every bucket, read through `entries`): fold them with a chain of XYZZ mixed additions.  Threads
-// walk the buckets in sorted order, so the lanes of a warp run chains of equal length.
-template <class F>
-__global__ void __launch_bounds__(128) k_tree_finish(TreeArgs<F> a) {
-    const int R = a.r;   // number of tree rounds done
-    const uint32_t min_c = R == 0 ? 1u : (1u << R) + 1u;
-    const uint32_t NQ = a.first[VB_CLASSES - min_c];   // buckets with size >= min_c
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < NQ; q += gridDim.x * blockDim.x) {
-        const uint32_t d = class_of(a.first, q);
-        const uint32_t c = VB_CLASSES - 1 - d, g = q - a.first[d];
-        const uint32_t m = tree_size_after(c, R);
-        const uint32_t v = a.order[q];
-        const uint32_t base = R == 0 ? a.vb_start[v] : a.wp_in[d] + g * m;
-        XYZZ<F> acc = XYZZ<F>::inf();
-        Affine<F> p = tree_load(a, base);
-        for (uint32_t i = 0; i < m; i++) {
-            Affine<F> pn = p;
-            if (i + 1 < m) pn = tree_load(a, base + i + 1);   // next load in flight during the addition
-            acc.madd(p);
-            p = pn;
-        }
-        a.result_vb[v] = acc;
-    }
+    result_vb[v] = acc;
 }
 
 template <class P>
@@ -549,30 +340,44 @@ __device__ __forceinline__ P shfl_down_point(const P& p, int delta) {
 }
 
 // Joins the partial sums of split (hot) buckets: result_vb[vbase[k]] = sum of the bucket's pieces.
+// Typical case (the buckets fed by a short top window, a few pieces each): one WARP per bucket.
+// Extreme skew (one bucket holding 30 % of a 2^22-point MSM is thousands of pieces): one CTA per
+// bucket (WIDE = true), launched over the same list; each kernel skips the other's buckets.
 constexpr int MSM_JOIN_THREADS = 128;
-template <class F>
+constexpr uint32_t MSM_JOIN_WIDE = 128;   // pieces above which a bucket is joined by a whole CTA
+template <class F, bool WIDE>
 __global__ void __launch_bounds__(MSM_JOIN_THREADS)
 k_vb_join(const uint32_t* __restrict__ hot_count, const uint32_t* __restrict__ hot_list, uint32_t hot_cap,
           const uint32_t* __restrict__ vbase, XYZZ<F>* __restrict__ result_vb) {
     __shared__ XYZZ<F> sh[MSM_JOIN_THREADS / 32];
     const uint32_t nhot = min(*hot_count, hot_cap);
-    for (uint32_t h = blockIdx.x; h < nhot; h += gridDim.x) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t unit = WIDE ? blockIdx.x : blockIdx.x * (MSM_JOIN_THREADS / 32) + wid;
+    const uint32_t nunits = WIDE ? gridDim.x : gridDim.x * (MSM_JOIN_THREADS / 32);
+    const uint32_t tid = WIDE ? threadIdx.x : lane, step = WIDE ? MSM_JOIN_THREADS : 32;
+    for (uint32_t h = unit; h < nhot; h += nunits) {
         const uint32_t k = hot_list[h];
         const uint32_t v0 = vbase[k], v1 = vbase[k + 1];
+        if ((v1 - v0 > MSM_JOIN_WIDE) != WIDE) continue;   // uniform over the unit
         XYZZ<F> acc = XYZZ<F>::inf();
-        for (uint32_t v = v0 + threadIdx.x; v < v1; v += MSM_JOIN_THREADS) acc.add(result_vb[v]);
+        for (uint32_t v = v0 + tid; v < v1; v += step) acc.add(result_vb[v]);
+        const int top = WIDE ? 16 : (v1 - v0 > 16 ? 16 : (v1 - v0 > 8 ? 8 : (v1 - v0 > 4 ? 4 : (v1 - v0 > 2 ? 2 : 1))));
 #pragma unroll 1
-        for (int dlt = 16; dlt >= 1; dlt >>= 1) {
+        for (int dlt = top; dlt >= 1; dlt >>= 1) {
             XYZZ<F> o = shfl_down_point(acc, dlt);
             acc.add(o);
         }
-        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < MSM_JOIN_THREADS / 32; w++) acc.add(sh[w]);
-            result_vb[v0] = acc;
+        if (!WIDE) {
+            if (lane == 0) result_vb[v0] = acc;
+        } else {
+            if (lane == 0) sh[wid] = acc;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int w = 1; w < MSM_JOIN_THREADS / 32; w++) acc.add(sh[w]);
+                result_vb[v0] = acc;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -747,11 +552,11 @@ class MsmRunner {
     void release();
     // kernels launched by the last run() (for bench.py's gpu_launches)
     int launches = 0;
-    KernelProfiler* prof = nullptr;   // optional: times the accumulation (tree rounds + finish)
+    KernelProfiler* prof = nullptr;   // optional: times the accumulate kernel
 
    private:
     enum { S_COUNTS, S_STARTS, S_TILES, S_ENTRIES, S_NV, S_VBASE, S_VBSTART, S_VBSIZE, S_ORDER, S_TABLES, S_HOT,
-           S_X0, S_X1, S_PREFIX, S_TOTALS, S_TSCRATCH, S_RESULT, S_SEGACC, S_SEGRUN, S_PARTS, S_COUNT };
+           S_RESULT, S_SEGACC, S_SEGRUN, S_PARTS, S_COUNT };
     MsmScratch s[S_COUNT];
 };
 

@@ -405,6 +405,7 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
         return G16_E_ARG;
     }
     G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
     std::unique_ptr<g16_circuit> c(new g16_circuit());
     c->ctx = ctx;
     G16_TRY(parse_ccs(ccs, ccs_len, &c->circ));
@@ -546,7 +547,16 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
     return G16_OK;
 }
 
-void g16_circuit_free(g16_circuit* c) { delete c; }
+void g16_circuit_free(g16_circuit* c) {
+    if (!c) return;
+    g16_ctx* ctx = c->ctx;
+    if (ctx) {
+        G16_LOCK(ctx);
+        delete c;
+    } else {
+        delete c;
+    }
+}
 
 const char* g16_circuit_solver(const g16_circuit* c) {
     if (!c) return "";
@@ -574,6 +584,7 @@ int g16_prove_wires_dev(g16_circuit* c, size_t n, const void* d_wires, const uin
         return G16_E_ARG;
     }
     G16_CUDA(cudaSetDevice(c->ctx->device));
+    G16_LOCK(c->ctx);
     cudaStream_t st = c->ctx->stream;
     // blinding scalars: injected (tests, benchmarks) or drawn from the OS CSPRNG -- never silently zero
     std::vector<HFr> extras(X_COUNT * n);
@@ -625,6 +636,7 @@ int g16_prove_wires(g16_circuit* c, size_t n, const uint8_t* wires_be, const uin
         return G16_E_ARG;
     }
     G16_CUDA(cudaSetDevice(c->ctx->device));
+    G16_LOCK(c->ctx);
     const size_t plen = c->has_commitment ? 388 : 324;
     for (size_t done = 0; done < n;) {
         size_t B = std::min(c->max_batch, n - done);
@@ -847,6 +859,7 @@ int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, siz
         return G16_E_ARG;
     }
     G16_CUDA(cudaSetDevice(c->ctx->device));
+    G16_LOCK(c->ctx);
     cudaStream_t st = c->ctx->stream;
     const size_t plen = c->has_commitment ? 388 : 324;
     // groups of solve_batch proofs are solved together (stage A); each group is proved in chunks of
@@ -933,6 +946,7 @@ int g16_witness_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, s
         set_error("g16_witness_batch: assignment size mismatch");
         return G16_E_ARG;
     }
+    G16_LOCK(c->ctx);
     for (size_t done = 0; done < n;) {
         size_t B = std::min(c->solve_batch, n - done);
         StageResult sr = stage_solve(c, 0, B, assignments_be + done * nin * 32, rnd ? rnd + 96 * done : nullptr, done, false);

@@ -109,6 +109,7 @@ extern "C" int g16_setup(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const
         return G16_E_ARG;
     }
     G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
     Circuit c;
     G16_TRY(parse_ccs(ccs, ccs_len, &c));
     if (c.commitments.size() > 1) {

@@ -58,6 +58,7 @@ extern "C" int g16_generate_points(g16_ctx* ctx, int g2, uint64_t seed, size_t n
         return G16_E_ARG;
     }
     G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
     size_t ptsz = g2 ? sizeof(G2Affine) : sizeof(G1Affine);
     G16_TRY(ctx->results.ensure(ptsz * n));
     if (!g2) {
