@@ -169,6 +169,21 @@ int g16_solve_assignment(const uint8_t* ccs, size_t ccs_len, const uint8_t* assi
                          const uint8_t* blinder_be, const uint8_t* challenges_be, size_t n_challenges,
                          uint8_t* wires_be, size_t wires_cap, uint8_t* committed_be, size_t committed_cap);
 
+/* ---- one large proof across several GPUs (BASELINE.json configs[3]) ----------------
+ * One process per GPU.  Rank 0 draws an id (g16_comm_unique_id) and hands it to the others (any channel:
+ * torch.distributed broadcast, a file, MPI); every rank then calls g16_comm_init on its context.  A circuit
+ * loaded on such a context keeps only this rank's contiguous index range of every MSM point set;
+ * g16_prove_wires / g16_prove_wires_dev become COLLECTIVE calls (same wires on every rank): each rank
+ * runs SpMV + H on its own copy and Pippenger on its slice, the partial G1 / G2 sums are combined with one
+ * NCCL all-gather of a few hundred bytes and every rank returns the same proof bytes.  Batches of
+ * independent proofs need none of this: they shard by proof with no collective. */
+int g16_comm_unique_id(uint8_t id[128]);
+int g16_comm_init(g16_ctx* ctx, const uint8_t id[128], int rank, int world);
+/* Synthetic constraint system in gnark's .ccs container (row k: (w_p)(sum_5 b_j w_qj) = w_new), generated
+ * natively because configs[3] needs 2^22 rows.  Two-call pattern: out = NULL returns the size. */
+int g16_synth_ccs(uint64_t n_constraints, uint32_t n_public, uint32_t n_secret, uint64_t seed, uint8_t* out,
+                  size_t* out_len);
+
 /* ---- verification (host only, no GPU needed) ------------------------------------------------- */
 /* `sunspot verify <vk> <proof> <pw>` (noir_circuit/prove_linux.sh:87, audit_circuit/prove_audit.sh:99):
  * gnark groth16.Verify incl. the BSB22 commitment and its Pedersen proof of knowledge.

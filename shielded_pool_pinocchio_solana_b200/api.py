@@ -30,6 +30,11 @@ class Context:
         except Exception:
             pass
 
+    def comm_init(self, unique_id: bytes, rank, world):
+        """Join the NCCL communicator of a single-proof-across-GPUs run (g16_comm_init)."""
+        assert len(unique_id) == 128
+        check(self.lib.g16_comm_init(self.handle, unique_id, rank, world))
+
     def set_stream(self, cuda_stream):
         check(self.lib.g16_set_stream(self.handle, ctypes.c_void_p(cuda_stream)))
 
@@ -210,6 +215,23 @@ def solve_assignment(ccs: bytes, assignment_be: bytes, nb_wires, blinder_be=None
     check(lib.g16_solve_assignment(ccs, len(ccs), assignment_be, len(assignment_be) // 32, blinder_be, challenges_be,
                                    len(challenges_be) // 32, wires, len(wires), committed, n_committed * 32))
     return wires.raw, committed.raw[:n_committed * 32]
+
+
+def comm_unique_id() -> bytes:
+    """NCCL unique id (rank 0 draws it, every rank passes it to Context.comm_init)."""
+    buf = ctypes.create_string_buffer(128)
+    check(_lib.load().g16_comm_unique_id(buf))
+    return buf.raw
+
+
+def synth_ccs(n_constraints, n_public=2, n_secret=64, seed=0x5EED22) -> bytes:
+    """Large synthetic circuit in the gnark .ccs container, generated natively."""
+    lib = _lib.load()
+    ln = ctypes.c_size_t(0)
+    check(lib.g16_synth_ccs(n_constraints, n_public, n_secret, seed, None, ctypes.byref(ln)))
+    buf = ctypes.create_string_buffer(ln.value)
+    check(lib.g16_synth_ccs(n_constraints, n_public, n_secret, seed, buf, ctypes.byref(ln)))
+    return buf.raw[:ln.value]
 
 
 def verify(vk: bytes, proof: bytes, pw: bytes) -> bool:

@@ -179,6 +179,7 @@ void g16_shutdown(g16_ctx* ctx) {
     ctx->g1.release();
     ctx->g2.release();
     ctx->ntt.release();
+    comm_release(ctx);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

@@ -22,6 +22,8 @@ void g1_from_be(const uint8_t* be, G1Affine* out);
 void g1_to_be(const G1Affine& p, uint8_t* be);
 void g2_from_be(const uint8_t* be, G2Affine* out);
 void g2_to_be(const G2Affine& p, uint8_t* be);
+// [lo, hi) of rank `rank` among `world` over n items
+void shard_range(size_t n, int rank, int world, size_t* lo, size_t* hi);
 
 }  // namespace g16
 
@@ -43,7 +45,18 @@ struct g16_ctx {
     g16::NttEngine ntt;
     g16::KernelProfiler prof;
     g16::DeviceBuf scratch, scalars, results;
+    // multi-GPU single proof (comm.cu): NCCL communicator (opaque), this context's slice of every MSM
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+    g16::DeviceBuf comm_recv;
 };
+
+namespace g16 {
+// d_pts[i] <- sum over the ranks of d_pts[i] (NCCL all-gather + add); no-op for world == 1
+template <class F>
+int comm_sum_points(g16_ctx* ctx, Affine<F>* d_pts, size_t count, cudaStream_t st);
+void comm_release(g16_ctx* ctx);
+}  // namespace g16
 
 struct g16_bases {
     int g2 = 0;

@@ -354,6 +354,11 @@ int prove_device(g16_circuit* c, size_t B, const Fr* W) {
         G16_CUDA(cudaStreamWaitEvent(st, c->ev_join[0], 0));
         G16_CUDA(cudaStreamWaitEvent(st, c->ev_join[1], 0));
     }
+    if (ctx->world > 1) {   // partial sums of this rank's point ranges -> sums over all ranks (tiny NCCL all-gather)
+        G16_TRY(comm_sum_points<Fp>(ctx, c->d_tmp_g1, 4 * c->max_batch, st));
+        G16_TRY(comm_sum_points<Fp2>(ctx, c->d_tmp_g2, c->max_batch, st));
+        launches += 2;
+    }
     k_finalize<<<(unsigned)B, 32, 0, st>>>(rA, rB1, c->d_tmp_g2, rKZ, rPok, W, c->wstride, c->nw,
                                            (ProofPoints*)c->d_out.ptr);
     launches++;
@@ -470,6 +475,30 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
         }
         mapPok = c->committed_wires;
     }
+    c->n_committed_total = c->n_committed;
+    // ---- single large proof across GPUs: this rank keeps one contiguous index range
+    // of every MSM point set; partial sums are all-gathered before the final assembly (comm.cu)
+    c->world = ctx->world;
+    if (ctx->world > 1) {
+        auto cut = [&](auto& pts, std::vector<uint32_t>* map) -> bool {
+            size_t lo, hi;
+            shard_range(pts.size(), ctx->rank, ctx->world, &lo, &hi);
+            if (hi <= lo) return false;
+            if (map) *map = std::vector<uint32_t>(map->begin() + lo, map->begin() + hi);
+            pts = std::decay_t<decltype(pts)>(pts.begin() + lo, pts.begin() + hi);
+            return true;
+        };
+        bool ok = cut(basesA, &mapA) && cut(basesB1, nullptr) && cut(basesB2, &mapB) && cut(basesKZ, &mapKZ);
+        if (ok && c->has_commitment) {
+            auto& key = pkh.commitment_keys[0];
+            ok = cut(key.basis, &c->committed_wires) && cut(key.basis_exp_sigma, &mapPok);
+            c->n_committed = c->committed_wires.size();
+        }
+        if (!ok) {
+            set_error("g16_circuit_load: an MSM point set is smaller than the number of ranks");
+            return G16_E_ARG;
+        }
+    }
     // ---- batch size: bounded by scratch memory (entries dominate: 4 B per base, window and proof)
     size_t max_batch = 64;
     if (c->n >= (1u << 18)) max_batch = 1;
@@ -540,6 +569,8 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
     }
     G16_CUDA(cudaMalloc(&c->d_tmp_g1, sizeof(G1Affine) * 4 * max_batch));
     G16_CUDA(cudaMalloc(&c->d_tmp_g2, sizeof(G2Affine) * max_batch));
+    G16_CUDA(cudaMemsetAsync(c->d_tmp_g1, 0, sizeof(G1Affine) * 4 * max_batch, st));   // unused slots = infinity
+    G16_CUDA(cudaMemsetAsync(c->d_tmp_g2, 0, sizeof(G2Affine) * max_batch, st));
     const NttDomain* dom;
     G16_TRY(ctx->ntt.domain(c->logn, st, &dom));
     G16_CUDA(cudaStreamSynchronize(st));
@@ -572,7 +603,7 @@ int g16_circuit_info(const g16_circuit* c, uint64_t what[16]) {
     what[3] = c->circ.nb_secret;
     what[4] = c->n;
     what[5] = c->circ.commitments.size();
-    what[6] = c->nA; what[7] = c->nB; what[8] = c->nK; what[9] = c->nZ; what[10] = c->n_committed;
+    what[6] = c->nA; what[7] = c->nB; what[8] = c->nK; what[9] = c->nZ; what[10] = c->n_committed_total;
     what[11] = c->max_batch;
     what[12] = c->bA.cfg.c; what[13] = c->bB1.cfg.c; what[14] = c->bKZ.cfg.c; what[15] = c->bB2.cfg.c;
     return G16_OK;
@@ -672,6 +703,7 @@ int g16_prove_wires(g16_circuit* c, size_t n, const uint8_t* wires_be, const uin
             G16_CUDA(cudaMemcpyAsync(sl.d_commit_vals.ptr, cv.data(), sizeof(Fr) * cv.size(), cudaMemcpyHostToDevice, st));
             G16_TRY(c->ctx->g1.run(c->bCommit, (const Fr*)sl.d_commit_vals.ptr, c->n_committed, nullptr, 1, B,
                                    (G1Affine*)sl.d_commit_out.ptr, st));
+            G16_TRY(comm_sum_points<Fp>(c->ctx, (G1Affine*)sl.d_commit_out.ptr, B, st));
             size_t nfp = B * 2;
             k_fp_from_mont<<<cdiv(nfp, 256), 256, 0, st>>>((Fp*)sl.d_commit_out.ptr, nfp);
             G16_CUDA(cudaMemcpyAsync(commits.data(), sl.d_commit_out.ptr, sizeof(G1Affine) * B, cudaMemcpyDeviceToHost, st));
@@ -860,6 +892,11 @@ int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, siz
     }
     G16_CUDA(cudaSetDevice(c->ctx->device));
     G16_LOCK(c->ctx);
+    if (c->world > 1) {
+        set_error("g16_prove_batch: this circuit is split across ranks (g16_comm_init): call g16_prove_wires / "
+                  "g16_prove_wires_dev collectively on every rank");
+        return G16_E_ARG;
+    }
     cudaStream_t st = c->ctx->stream;
     const size_t plen = c->has_commitment ? 388 : 324;
     // groups of solve_batch proofs are solved together (stage A); each group is proved in chunks of

@@ -51,7 +51,9 @@ struct g16_circuit {
     size_t solve_batch = 0;    // proofs per witness-solve batch (a multiple of max_batch)
     bool has_commitment = false;
     int unit_ids = 0;       // coefficient ids 0/1/3 are 0/+1/-1 (gnark's fixed table prefix)
-    size_t n_committed = 0;
+    size_t n_committed = 0;        // committed wires held by THIS rank (all of them unless the circuit is split)
+    size_t n_committed_total = 0;
+    int world = 1;                 // > 1: MSM point sets are split across ranks
     std::vector<uint32_t> committed_wires;
     // R1CS on the device: three CSR matrices sharing one coefficient table
     uint32_t* d_rowptr[3] = {nullptr, nullptr, nullptr};

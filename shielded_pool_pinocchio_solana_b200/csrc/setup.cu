@@ -200,6 +200,20 @@ extern "C" int g16_setup(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const
     for (uint32_t x : committed) s1.push_back(t[x] * ginv);
     for (uint32_t x : committed) s1.push_back(t[x] * ginv * sigma);
     if (!c.commitments.empty()) { s2.push_back(g2k); s2.push_back((sigma * g2k).neg()); }
+    // ---- size query: everything below only fills bytes whose count is already known ---------------
+    {
+        const size_t ncom = c.commitments.size();
+        const size_t need_pk = 8 + 5 * 32 + 1 + 3 * 64 + (4 + nA * 64) + (4 + nB * 64) + (4 + (n - 1) * 64) + (4 + nK * 64) +
+                               2 * 128 + (4 + nB * 128) + 3 * 8 + 2 * (4 + nw) + 4 + (ncom ? 2 * (4 + committed.size() * 64) : 0);
+        size_t need_vk = 2 * 64 + 2 * 128 + 64 + 128 + 4 + nVk * 64 + 4 + 4;
+        for (auto& info : c.commitments) need_vk += 4 + 8 * info.public_and_commitment_committed.size();
+        if (ncom) need_vk += 2 * 128;
+        if (!pk_out && !vk_out) {
+            *pk_len = need_pk;
+            *vk_len = need_vk;
+            return G16_OK;
+        }
+    }
     // ---- device: fixed-base multiplications ------------------------------------------------------
     cudaStream_t st = ctx->stream;
     std::vector<HFr> c1(s1.size()), c2(s2.size());

@@ -179,3 +179,33 @@ def test_noir_witness_front_door_and_cli(ctx, tmp_path):
     assert len(proof) == 388 and G.verify(G.read_vk(vk), proof, pw)
     bad = subprocess.run([exe, "prove", str(d / "c.json"), str(d / "c.ccs"), str(d / "c.ccs"), str(d / "c.pk")], capture_output=True)
     assert bad.returncode != 0 and b"witness" in bad.stderr
+
+
+def test_native_synth_circuit_and_split_context_world1(ctx):
+    """BASELINE.json configs[3] plumbing on one GPU: the natively generated synthetic circuit (g16_synth_ccs) is
+    set up, solved, proved and verified; a context that joined a (1-rank) NCCL communicator takes the split-proof
+    path (slice = everything, all-gather of one rank) and returns the same bytes."""
+    import random
+    ccs = g16.synth_ccs(1 << 12, 2, 64, 99)
+    pk, vk = ctx.setup(ccs, b"split-test")
+    circ = ctx.load_circuit(ccs, pk)
+    assert circ.info["nb_constraints"] == 4096 and circ.info["nb_commitments"] == 0 and circ.proof_len == 324
+    rng = random.Random(5)
+    asg = b"".join(rng.randrange(synth_R()).to_bytes(32, "big") for _ in range(66))
+    rnd = bytes(range(3, 99))
+    proof, pw = circ.prove_assignment(asg, rnd)
+    assert g16.verify(vk, proof, pw)
+    wires, _ = g16.solve_assignment(ccs, asg, circ.info["nb_wires"])
+    assert circ.prove_wires(wires, 1, rnd) == [proof]
+    circ.free()
+    split = g16.Context(0)
+    split.comm_init(g16.comm_unique_id(), 0, 1)
+    c1 = split.load_circuit(ccs, pk)
+    assert c1.prove_wires(wires, 1, rnd) == [proof]
+    c1.free()
+    split.close()
+
+
+def synth_R():
+    from shielded_pool_pinocchio_solana_b200 import synth
+    return synth.R
