@@ -394,18 +394,20 @@ def main():
         return sum(step_dev(i, which) for i in range(args.steps))
 
     asg_all = b"".join(asg_a[i % n_sets] for i in range(args.steps))
+    wires_all = b"".join(host_w[i % n_sets] for i in range(args.steps))
+    rnd_w_all = rnd_w * args.steps
 
     def run_e2e(which="wa"):
-        # audit: ONE g16_prove_batch call for all K steps' proofs (the library pipelines solve and prove of
-        # consecutive chunks, what a caller with K*B pending proofs does); withdraw: one g16_prove_wires per step
+        # ONE call per circuit for all K steps' proofs (what a caller with K*B pending proofs does): the library
+        # pipelines stage A (audit: H2D of the assignments, device witness solver, commitment; withdraw: H2D of the
+        # big-endian wire vectors, conversion, commitment) of one group with the proving of the previous one
         n = 0
         if "a" in which:
             circ_a.prove_batch(asg_all, B * args.steps)
             n += ctx.last_launches()
         if "w" in which:
-            for i in range(args.steps):
-                circ_w.prove_wires(host_w[i % n_sets], B, rnd_w)
-                n += ctx.last_launches()
+            circ_w.prove_wires(wires_all, B * args.steps, rnd_w_all)
+            n += ctx.last_launches()
         return n
 
     def timed(fn):
@@ -442,7 +444,8 @@ def main():
     ctx.profile_enable(False)
     # warm-up with the group size the timed call uses (scratch buffers grow on first use)
     circ_a.prove_batch(asg_all[:min(args.steps, 8) * B * circ_a.n_values * 32], min(args.steps, 8) * B)
-    circ_w.prove_wires(host_w[0], B, rnd_w)
+    circ_w.prove_wires(wires_all[:min(args.steps, 8) * B * circ_w.info["nb_wires"] * 32], min(args.steps, 8) * B,
+                       rnd_w_all[:min(args.steps, 8) * B * 96])
     results["e2e"], _ = timed(run_e2e)
     results["e2e_audit"], _ = timed(lambda: run_e2e("a"))
 

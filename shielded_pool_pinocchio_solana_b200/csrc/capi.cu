@@ -4,6 +4,9 @@
 
 #include <string.h>
 
+#include <chrono>
+#include <functional>
+#include <thread>
 #include <vector>
 
 namespace g16 {
@@ -11,6 +14,14 @@ namespace g16 {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* get_error() { return g_err.c_str(); }
+
+void trace(const char* tag, long a) {
+    static const bool on = getenv("G16_TRACE") && atoi(getenv("G16_TRACE")) != 0;
+    if (!on) return;
+    static const auto t0 = std::chrono::steady_clock::now();
+    long us = (long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[g16 %9ld us t%04x] %s %ld\n", us, (unsigned)(std::hash<std::thread::id>()(std::this_thread::get_id()) & 0xffff), tag, a);
+}
 
 // ---- byte-order helpers (gnark wire formats <-> little-endian limbs) ---------------------------
 void be32_to_limbs(const uint8_t* be, uint32_t* limbs) {

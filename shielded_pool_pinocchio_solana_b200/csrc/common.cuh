@@ -14,6 +14,8 @@ namespace g16 {
 // Thread-local last error, surfaced through g16_last_error() (include/g16b200.h).
 void set_error(const std::string& msg);
 const char* get_error();
+// G16_TRACE=1: host-side timestamps (us since the first call, thread id) of pipeline stages on stderr
+void trace(const char* tag, long a = 0);
 
 
 #define G16_CUDA(expr)                                                                       \

@@ -4,8 +4,13 @@
 // gnark walks the instruction levels with goroutines; on a 16-core host that costs 10-20 ms per
 // audit-size proof and caps a box at a few hundred proofs/s -- less than ONE B200 proves.  Here the
 // level structure is compiled once per circuit into a static plan (which wire each row defines is
-// independent of the witness), and a CTA per proof executes it: threads take the instructions of a
-// level, __syncthreads() separates levels, wires live in HBM in the layout the prover reads.
+// independent of the witness), and ONE WARP per proof executes it: lanes take the instructions of a
+// level (median ~20 per level in the reference circuit), __syncwarp() separates levels, wires live in
+// HBM in the layout the prover reads.  The solve is latency-bound (~10^3 dependent levels), so the
+// plan is flattened into per-level records (one 32-byte record per instruction, then its terms) to keep
+// the chain of dependent loads at record -> terms -> wires, the terms of a row are fetched four at a
+// time so their loads and products overlap, and eight proofs share a CTA so that the solver occupies
+// few SMs while the proving kernels of the previous group run beside it.
 // The BSB22 commitment splits the plan in two phases (prove.cu runs the commitment MSM between).
 // Circuits using a hint this file does not implement keep the host solver (solver.cpp).
 #include "gpusolver.cuh"
@@ -167,6 +172,84 @@ k_solve_levels(const uint32_t* __restrict__ lvl_off, const uint32_t* __restrict_
     }
 }
 
+// ---- warp-per-proof variant -------------------------------------------------------------------
+constexpr int SOLVE_WARPS = 8;   // proofs per CTA
+
+// rec[2k]   = (mode, defined wire, coefficient id of the defined wire's term, constraint row)
+// rec[2k+1] = (calldata offset of the instruction, nL, nR, nO)          k = position in level order
+__global__ void __launch_bounds__(32 * SOLVE_WARPS)
+k_solve_warp(const uint32_t* __restrict__ lvl_off, const uint4* __restrict__ rec, const uint32_t* __restrict__ calldata,
+             const Fr* __restrict__ coeffs, const Fr* __restrict__ coeff_invs, Fr* wires, size_t wstride,
+             size_t blinder_slot, uint32_t nproofs, uint32_t lvl_begin, uint32_t lvl_end, int unit_ids, uint32_t* err) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * SOLVE_WARPS + (threadIdx.x >> 5);
+    if (b >= nproofs) return;   // whole warp
+    Fr* w = wires + (size_t)b * wstride;
+    uint32_t* e = err + b;
+    for (uint32_t lv = lvl_begin; lv < lvl_end; lv++) {
+        const uint32_t s = lvl_off[lv], t = lvl_off[lv + 1];
+        for (uint32_t k = s + lane; k < t; k += 32) {
+            const uint4 inf = rec[2 * k], shp = rec[2 * k + 1];
+            const uint32_t* cd = calldata + shp.x;
+            if (inf.x >= 16) {
+                run_hint(inf.x - 16, cd, w, coeffs, unit_ids, w[blinder_slot], e);
+                continue;
+            }
+            const uint32_t nl = shp.y, nlr = shp.y + shp.z, nt = nlr + shp.w;
+            const uint32_t skip = inf.x == 0 ? NO_WIRE : inf.y;
+            const uint32_t* terms = cd + 4;
+            Fr L = Fr::zero(), Rr = Fr::zero(), O = Fr::zero();
+            for (uint32_t i0 = 0; i0 < nt; i0 += 4) {
+                uint32_t cid[4], wid[4];
+                Fr x[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool in = i0 + j < nt;
+                    cid[j] = in ? terms[2 * (i0 + j)] : 0u;
+                    wid[j] = in ? terms[2 * (i0 + j) + 1] : skip;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    // kind: 0 skip, 1 +x, 2 -x, 3 c*x, 4 +c (constant term)
+                    x[j] = Fr::zero();
+                    if (i0 + j < nt && wid[j] != skip && wid[j] != CCS_CONST_WIRE) x[j] = w[wid[j]];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (i0 + j >= nt || wid[j] == skip) continue;
+                    Fr v;
+                    if (wid[j] == CCS_CONST_WIRE) v = coeffs[cid[j]];
+                    else if (unit_ids && cid[j] == 1) v = x[j];
+                    else if (unit_ids && cid[j] == 3) v = x[j].neg();
+                    else if (unit_ids && cid[j] == 0) continue;
+                    else v = coeffs[cid[j]] * x[j];
+                    const uint32_t i = i0 + j;
+                    if (i < nl) L = L + v;
+                    else if (i < nlr) Rr = Rr + v;
+                    else O = O + v;
+                }
+            }
+            if (inf.x == 0) {
+                if (L * Rr != O) atomicMin(e, inf.w + 1);           // constraint row (1-based)
+            } else if (inf.x == 1) {
+                w[inf.y] = (L * Rr - O) * coeff_invs[inf.z];
+            } else if (inf.x == 2) {
+                // zero divisor: gnark leaves the wire at 0 and only checks the row (0 == O)
+                if (Rr.is_zero()) {
+                    if (!O.is_zero()) atomicMin(e, inf.w + 1);
+                    w[inf.y] = Fr::zero();
+                } else w[inf.y] = (O * Rr.inverse() - L) * coeff_invs[inf.z];
+            } else {
+                if (L.is_zero()) {
+                    if (!O.is_zero()) atomicMin(e, inf.w + 1);
+                    w[inf.y] = Fr::zero();
+                } else w[inf.y] = (O * L.inverse() - Rr) * coeff_invs[inf.z];
+            }
+        }
+        __syncwarp();   // orders this level's wire stores before the next level's loads (same warp)
+    }
+}
+
 // assignment (big-endian canonical) -> wires[b][1..nin] (Montgomery), wire 0 = 1, X_* slots from rnd
 __global__ void __launch_bounds__(256)
 k_assign(const uint8_t* __restrict__ asg_be, const uint8_t* __restrict__ rnd_be, uint32_t nin, Fr* __restrict__ wires,
@@ -222,6 +305,8 @@ int upload(const std::vector<T>& v, T** d, cudaStream_t st) {
 void GpuSolverPlan::release() {
     cudaFree(d_lvl_off); cudaFree(d_lvl_instr); cudaFree(d_info); cudaFree(d_instr_cd); cudaFree(d_calldata);
     cudaFree(d_coeff_invs);
+    cudaFree(d_rec);
+    d_rec = nullptr;
     d_lvl_off = d_lvl_instr = d_instr_cd = d_calldata = nullptr;
     d_info = nullptr;
     d_coeff_invs = nullptr;
@@ -343,6 +428,14 @@ int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not
             return G16_OK;
         }
     nlevels = (uint32_t)c.levels.size();
+    std::vector<uint4> rec(2 * lvl_instr.size());
+    for (size_t k = 0; k < lvl_instr.size(); k++) {
+        const uint32_t ins = lvl_instr[k];
+        const uint32_t* cd = c.calldata.data() + c.start_calldata[ins];
+        rec[2 * k] = info[ins];
+        rec[2 * k + 1] = c.blueprint[ins] == 1 ? make_uint4(instr_cd[ins], cd[1], cd[2], cd[3]) : make_uint4(instr_cd[ins], 0, 0, 0);
+    }
+    G16_TRY(upload(rec, &d_rec, st));
     G16_TRY(upload(lvl_off, &d_lvl_off, st));
     G16_TRY(upload(lvl_instr, &d_lvl_instr, st));
     G16_TRY(upload(info, &d_info, st));
@@ -366,9 +459,15 @@ int GpuSolverPlan::assign(const uint8_t* d_asg_be, const uint8_t* d_rnd_be, uint
 int GpuSolverPlan::run(const Fr* d_coeffs, int unit_ids, Fr* d_wires, size_t wstride, size_t nw, size_t B,
                        uint32_t lvl_begin, uint32_t lvl_end, uint32_t* d_err, cudaStream_t st) const {
     if (lvl_begin >= lvl_end) return G16_OK;
-    k_solve_levels<<<(unsigned)B, SOLVE_THREADS, 0, st>>>(d_lvl_off, d_lvl_instr, d_info, d_instr_cd, d_calldata, d_coeffs,
-                                                          d_coeff_invs, d_wires, wstride, nw + X_BLINDER, lvl_begin,
-                                                          lvl_end, unit_ids, d_err);
+    static const bool cta_per_proof = getenv("G16_SOLVER_CTA") && atoi(getenv("G16_SOLVER_CTA")) != 0;   // round-1 kernel
+    if (cta_per_proof)
+        k_solve_levels<<<(unsigned)B, SOLVE_THREADS, 0, st>>>(d_lvl_off, d_lvl_instr, d_info, d_instr_cd, d_calldata, d_coeffs,
+                                                              d_coeff_invs, d_wires, wstride, nw + X_BLINDER, lvl_begin,
+                                                              lvl_end, unit_ids, d_err);
+    else
+        k_solve_warp<<<cdiv(B, SOLVE_WARPS), 32 * SOLVE_WARPS, 0, st>>>(d_lvl_off, d_rec, d_calldata, d_coeffs, d_coeff_invs,
+                                                                        d_wires, wstride, nw + X_BLINDER, (uint32_t)B,
+                                                                        lvl_begin, lvl_end, unit_ids, d_err);
     G16_CUDA(cudaGetLastError());
     return G16_OK;
 }

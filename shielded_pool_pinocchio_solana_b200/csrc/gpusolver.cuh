@@ -19,6 +19,7 @@ struct GpuSolverPlan {
     uint32_t commit_wire = 0;
     uint32_t *d_lvl_off = nullptr, *d_lvl_instr = nullptr, *d_instr_cd = nullptr, *d_calldata = nullptr;
     uint4* d_info = nullptr;
+    uint4* d_rec = nullptr;                 // flattened plan: two uint4 per instruction, in level order
     Fr* d_coeff_invs = nullptr;
 
     // Compiles the plan; leaves valid == false (and says why) when the circuit needs the host solver.

@@ -167,6 +167,44 @@ k_r1cs_spmv(const uint32_t* __restrict__ rp0, const uint32_t* __restrict__ cid0,
     abc[((size_t)proof * 3 + m) * n + row] = acc;
 }
 
+// 32 big-endian bytes (32-byte aligned) -> canonical little-endian limbs, reduced below r
+__device__ __forceinline__ Fr fr_load_be(const uint4* __restrict__ p) {
+    const uint4 hi = p[0], lo = p[1];
+    Fr f;
+    f.v[7] = __byte_perm(hi.x, 0, 0x0123); f.v[6] = __byte_perm(hi.y, 0, 0x0123);
+    f.v[5] = __byte_perm(hi.z, 0, 0x0123); f.v[4] = __byte_perm(hi.w, 0, 0x0123);
+    f.v[3] = __byte_perm(lo.x, 0, 0x0123); f.v[2] = __byte_perm(lo.y, 0, 0x0123);
+    f.v[1] = __byte_perm(lo.z, 0, 0x0123); f.v[0] = __byte_perm(lo.w, 0, 0x0123);
+    uint32_t m[8], d[8];
+    Fr::modulus(m);
+    for (int it = 0; it < 6; it++) {   // 256-bit inputs: at most 5 subtractions
+        if (ff_sub8(d, f.v, m)) break;
+#pragma unroll
+        for (int l = 0; l < 8; l++) f.v[l] = d[l];
+    }
+    return f;
+}
+
+// Full wire vectors as the caller holds them (big-endian, nw per proof) -> Montgomery wire vectors with
+// stride wstride; thread nw of every proof fills the X_* slots from rnd (r | s | unused), as k_assign does.
+__global__ void __launch_bounds__(256)
+k_wires_from_be(const uint4* __restrict__ wires_be, const uint4* __restrict__ rnd_be, Fr* __restrict__ wires,
+                size_t wstride, uint32_t nw) {
+    const uint32_t b = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    Fr* w = wires + (size_t)b * wstride;
+    if (i < nw) {
+        w[i] = fr_load_be(wires_be + ((size_t)b * nw + i) * 2).to_mont();
+    } else if (i == nw) {
+        const Fr r = fr_load_be(rnd_be + (size_t)b * 6).to_mont(), s = fr_load_be(rnd_be + (size_t)b * 6 + 2).to_mont();
+        w[nw + X_ONE] = Fr::one();
+        w[nw + X_R] = r;
+        w[nw + X_S] = s;
+        w[nw + X_NEG_RS] = (r * s).neg();
+        for (int k = X_NEG_RS + 1; k < X_COUNT; k++) w[nw + k] = Fr::zero();
+    }
+}
+
 __global__ void k_set_one(Fr* wires, size_t wstride, size_t slot, uint32_t n) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < n) wires[(size_t)b * wstride + slot] = Fr::one();
@@ -240,6 +278,10 @@ g16_circuit::~g16_circuit() {
         if (sl.h_wires) cudaFreeHost(sl.h_wires);
         if (sl.ready) cudaEventDestroy(sl.ready);
     }
+    for (int i = 0; i < 2; i++) {
+        if (h_pts[i]) cudaFreeHost(h_pts[i]);
+        if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+    }
     g1_aux.release();
     g1_side.release();
     g2_side.release();
@@ -261,7 +303,13 @@ int upload_vec(const std::vector<T>& v, T** d, cudaStream_t st) {
 }
 
 int random_fr(HFr* out) {
-    std::ifstream ur("/dev/urandom", std::ios::binary);
+    // one descriptor per thread, kept open: a 256-proof group draws 768 scalars
+    static thread_local std::ifstream ur("/dev/urandom", std::ios::binary);
+    if (!ur) {
+        ur.clear();
+        ur.close();
+        ur.open("/dev/urandom", std::ios::binary);
+    }
     for (int tries = 0; tries < 64; tries++) {
         uint8_t b[32];
         ur.read((char*)b, 32);
@@ -548,6 +596,10 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
         G16_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
     G16_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+        G16_CUDA(cudaMallocHost((void**)&c->h_pts[i], sizeof(ProofPoints) * max_batch));
+        G16_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
     for (auto& sl : c->slots) {
         G16_TRY(sl.d_wires.ensure(sizeof(Fr) * c->wstride * solve_batch));
         G16_TRY(sl.d_commit_vals.ensure(sizeof(Fr) * (c->n_committed ? c->n_committed : 1) * solve_batch));
@@ -661,19 +713,16 @@ static int prove_from_host_wires(g16_circuit* c, size_t n, const HFr* wires, con
     return G16_OK;
 }
 
-int g16_prove_wires(g16_circuit* c, size_t n, const uint8_t* wires_be, const uint8_t* rnd, uint8_t* proofs) {
-    if (!c || !wires_be || !proofs || n == 0) {
-        set_error("g16_prove_wires: bad arguments");
-        return G16_E_ARG;
-    }
-    G16_CUDA(cudaSetDevice(c->ctx->device));
-    G16_LOCK(c->ctx);
+// Synchronous variant: host conversion, one chunk at a time on the context stream.  Used when the circuit is
+// split across ranks (every call is then a collective and must enqueue its NCCL work in program order).
+static int prove_wires_sync(g16_circuit* c, size_t n, const uint8_t* wires_be, const uint8_t* rnd, uint8_t* proofs) {
     const size_t plen = c->has_commitment ? 388 : 324;
     for (size_t done = 0; done < n;) {
         size_t B = std::min(c->max_batch, n - done);
         std::vector<HFr> w(c->wstride * B);
         std::vector<G1Affine> commits(B, G1Affine::inf());
         std::vector<int> rcs(B, G16_OK);
+        trace("wires: convert begin", (long)done);
         parallel_for(B, [&](size_t b) {
             const uint8_t* src = wires_be + (done + b) * c->nw * 32;
             HFr* dst = w.data() + b * c->wstride;
@@ -688,6 +737,7 @@ int g16_prove_wires(g16_circuit* c, size_t n, const uint8_t* wires_be, const uin
             }
             fill_extras(dst, c->nw, r, s);
         });
+        trace("wires: converted");
         for (int rc : rcs)
             if (rc != G16_OK) {
                 set_error("could not read /dev/urandom");
@@ -709,7 +759,9 @@ int g16_prove_wires(g16_circuit* c, size_t n, const uint8_t* wires_be, const uin
             G16_CUDA(cudaMemcpyAsync(commits.data(), sl.d_commit_out.ptr, sizeof(G1Affine) * B, cudaMemcpyDeviceToHost, st));
             G16_CUDA(cudaStreamSynchronize(st));
         }
+        trace("wires: commitments done");
         G16_TRY(prove_from_host_wires(c, B, w.data(), c->has_commitment ? commits.data() : nullptr, proofs + plen * done));
+        trace("wires: proved");
         done += B;
     }
     return G16_OK;
@@ -826,6 +878,7 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
     uint8_t* h_rnd = h_asg + 32 * nin * c->solve_batch;
     HFr* h_chal = (HFr*)(h_rnd + 96 * c->solve_batch);
     uint32_t* h_err = (uint32_t*)((uint8_t*)h_chal + sizeof(HFr) * c->solve_batch);
+    trace("solve_gpu: begin", (long)first_index);
     memcpy(h_asg, assignments_be, 32 * nin * B);
     if (rnd) memcpy(h_rnd, rnd, 96 * B);
     else
@@ -834,6 +887,7 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
             if (random_fr(&v) != G16_OK) return failm(G16_E_INTERNAL, "could not read /dev/urandom");
             v.to_be(h_rnd + 32 * k);
         }
+    trace("solve_gpu: staged");
     Fr* W = (Fr*)sl.d_wires.ptr;
     uint32_t* d_err = (uint32_t*)sl.d_err.ptr;
     G16_STAGE_CUDA(cudaMemcpyAsync(sl.d_asg_be.ptr, h_asg, 32 * nin * B, cudaMemcpyHostToDevice, st));
@@ -849,13 +903,16 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
         rc = c->g1_aux.run(c->bCommit, W, c->wstride, c->d_map_commit, 1, B, (G1Affine*)sl.d_commit_out.ptr, st);
         if (rc != G16_OK) return failm(rc, get_error());
         k_fp_from_mont<<<cdiv(B * 2, 256), 256, 0, st>>>((Fp*)sl.d_commit_out.ptr, B * 2);
+        trace("solve_gpu: phase1 enqueued");
         G16_STAGE_CUDA(cudaMemcpyAsync(sl.commits.data(), sl.d_commit_out.ptr, sizeof(G1Affine) * B, cudaMemcpyDeviceToHost, st));
         G16_STAGE_CUDA(cudaStreamSynchronize(st));
+        trace("solve_gpu: phase1 done");
         for (size_t b = 0; b < B; b++) {
             uint8_t msg[64];
             g1_to_be(sl.commits[b], msg);
             h_chal[b] = hash_to_fr(msg, 64, "bsb22-commitment");
         }
+        trace("solve_gpu: challenges hashed");
         G16_STAGE_CUDA(cudaMemcpyAsync(sl.d_chal.ptr, h_chal, sizeof(Fr) * B, cudaMemcpyHostToDevice, st));
         if ((rc = c->plan.set_wire(W, c->wstride, c->plan.commit_wire, (const Fr*)sl.d_chal.ptr, B, st)) != G16_OK) return failm(rc, get_error());
         if ((rc = c->plan.run(c->d_coeffs, c->unit_ids, W, c->wstride, c->nw, B, split, c->plan.nlevels, d_err, st)) != G16_OK)
@@ -864,6 +921,7 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
     G16_STAGE_CUDA(cudaMemcpyAsync(h_err, d_err, 4 * B, cudaMemcpyDeviceToHost, st));
     G16_STAGE_CUDA(cudaEventRecord(sl.ready, st));
     G16_STAGE_CUDA(cudaStreamSynchronize(st));
+    trace("solve_gpu: done");
     for (size_t b = 0; b < B; b++)
         if (h_err[b] != 0xffffffffu) {
             if (h_err[b] & 0x80000000u) return failm(G16_E_HINT, "proof " + std::to_string(first_index + b) + ": solver hint failed on the device");
@@ -871,6 +929,168 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
         }
 #undef G16_STAGE_CUDA
     return res;
+}
+
+// ---- stage A for callers that already hold full wire vectors: big-endian wires -> slot.d_wires ----------
+static StageResult stage_wires(g16_circuit* c, int slot_id, size_t G, const uint8_t* wires_be, const uint8_t* rnd,
+                               size_t first_index) {
+    StageResult res;
+    auto failm = [&](int rc, const std::string& m) {
+        res.rc = rc;
+        res.err = m;
+        return res;
+    };
+#define G16_STAGE_CUDA(expr)                                                                  \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) return failm(G16_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+    G16_STAGE_CUDA(cudaSetDevice(c->ctx->device));
+    const size_t nin = c->circ.nb_public - 1 + c->circ.nb_secret;
+    g16_circuit::Slot& sl = c->slots[slot_id];
+    cudaStream_t st = c->aux_stream;
+    trace("wires: stage begin", (long)first_index);
+    const size_t bytes = 32 * c->nw * G;
+    if (sl.d_wires_be.ensure(bytes) != G16_OK) return failm(G16_E_CUDA, get_error());
+    // pageable caller memory -> pinned staging (threads), then one asynchronous copy
+    uint8_t* h_be = (uint8_t*)sl.h_wires;   // pinned, wstride * solve_batch * 32 bytes >= bytes
+    const size_t pieces = std::min<size_t>(G, 64), per = (bytes + pieces - 1) / pieces;
+    parallel_for(pieces, [&](size_t k) {
+        const size_t lo = k * per, hi = std::min(bytes, lo + per);
+        if (lo < hi) memcpy(h_be + lo, wires_be + lo, hi - lo);
+    });
+    uint8_t* h_rnd = (uint8_t*)sl.h_stage + 32 * nin * c->solve_batch;
+    if (rnd) {
+        memcpy(h_rnd, rnd, 96 * G);
+    } else {
+        for (size_t k = 0; k < 3 * G; k++) {   // never fall back to r = s = 0 (a non-zero-knowledge proof)
+            HFr v;
+            if (random_fr(&v) != G16_OK) return failm(G16_E_INTERNAL, "could not read /dev/urandom");
+            v.to_be(h_rnd + 32 * k);
+        }
+    }
+    trace("wires: staged");
+    G16_STAGE_CUDA(cudaMemcpyAsync(sl.d_wires_be.ptr, h_be, bytes, cudaMemcpyHostToDevice, st));
+    G16_STAGE_CUDA(cudaMemcpyAsync(sl.d_rnd_be.ptr, h_rnd, 96 * G, cudaMemcpyHostToDevice, st));
+    Fr* W = (Fr*)sl.d_wires.ptr;
+    k_wires_from_be<<<dim3(cdiv(c->nw + 1, 256), (unsigned)G), 256, 0, st>>>((const uint4*)sl.d_wires_be.ptr,
+                                                                            (const uint4*)sl.d_rnd_be.ptr, W, c->wstride,
+                                                                            (uint32_t)c->nw);
+    G16_STAGE_CUDA(cudaGetLastError());
+    sl.commits.assign(G, G1Affine::inf());
+    if (c->has_commitment) {   // commitment point = MSM of the committed wire values over the commitment basis
+        int rc = c->g1_aux.run(c->bCommit, W, c->wstride, c->d_map_commit, 1, G, (G1Affine*)sl.d_commit_out.ptr, st);
+        if (rc != G16_OK) return failm(rc, get_error());
+        k_fp_from_mont<<<cdiv(G * 2, 256), 256, 0, st>>>((Fp*)sl.d_commit_out.ptr, G * 2);
+        G16_STAGE_CUDA(cudaMemcpyAsync(sl.commits.data(), sl.d_commit_out.ptr, sizeof(G1Affine) * G, cudaMemcpyDeviceToHost, st));
+    }
+    G16_STAGE_CUDA(cudaEventRecord(sl.ready, st));
+    G16_STAGE_CUDA(cudaStreamSynchronize(st));
+    trace("wires: stage done");
+#undef G16_STAGE_CUDA
+    return res;
+}
+
+// ---- the two-stage pipeline shared by g16_prove_batch and g16_prove_wires ---------------------------------
+// `launch(g)` starts stage A of group g (solve_batch proofs -> slot g&1: device wires, commitments, `ready`
+// event); stage B proves the group in chunks of max_batch on the context stream.  Results return through two
+// pinned buffers: chunk k-1 is serialised on the host while the device proves chunk k.  `after(first, B)` runs
+// once the proofs [first, first+B) are written.
+}  // extern "C" (templates need C++ linkage)
+template <class Launch, class After>
+static int run_pipeline(g16_circuit* c, size_t n, Launch launch, uint8_t* proofs, After after) {
+    cudaStream_t st = c->ctx->stream;
+    const size_t plen = c->has_commitment ? 388 : 324;
+    const size_t SB = c->solve_batch;
+    const size_t ngroups = (n + SB - 1) / SB;
+    auto group_size = [&](size_t g) { return std::min(SB, n - g * SB); };
+    struct Pending {
+        bool live = false;
+        size_t first = 0, B = 0, off = 0;
+        int slot = 0, ring = 0;
+    } pend;
+    auto drain = [&]() -> int {
+        if (!pend.live) return G16_OK;
+        pend.live = false;
+        if (cudaEventSynchronize(c->ev_done[pend.ring]) != cudaSuccess) {
+            set_error(std::string("device pipeline: ") + cudaGetErrorString(cudaGetLastError()));
+            return G16_E_CUDA;
+        }
+        trace("pipeline: chunk done", (long)pend.first);
+        const ProofPoints* pts = c->h_pts[pend.ring];
+        const g16_circuit::Slot& sl = c->slots[pend.slot];
+        for (size_t b = 0; b < pend.B; b++)
+            write_proof_bytes(pts[b], c->has_commitment ? &sl.commits[pend.off + b] : nullptr, proofs + plen * (pend.first + b));
+        after(pend.first, pend.B);
+        return G16_OK;
+    };
+    std::future<StageResult> fut = launch((size_t)0);
+    int total_launches = 0, rc = G16_OK;
+    size_t chunk_no = 0;
+    for (size_t g = 0; g < ngroups && rc == G16_OK; g++) {
+        StageResult sr = fut.get();
+        if (sr.rc != G16_OK) {
+            set_error(sr.err);
+            rc = sr.rc;
+            break;
+        }
+        // the slot stage g+1 writes was last read by the chunk that may still be in flight
+        if ((rc = drain()) != G16_OK) break;
+        if (g + 1 < ngroups) fut = launch(g + 1);   // stage A of group g+1 runs while the device proves group g
+        g16_circuit::Slot& sl = c->slots[g & 1];
+        const size_t G = group_size(g);
+        if (cudaStreamWaitEvent(st, sl.ready, 0) != cudaSuccess) {
+            rc = G16_E_CUDA;
+            set_error("cudaStreamWaitEvent failed");
+        }
+        for (size_t off = 0; off < G && rc == G16_OK; off += c->max_batch) {
+            const size_t B = std::min(c->max_batch, G - off), first = g * SB + off;
+            const int ring = (int)(chunk_no++ & 1);
+            trace("pipeline: chunk begin", (long)first);
+            if ((rc = prove_device(c, B, (const Fr*)sl.d_wires.ptr + off * c->wstride)) != G16_OK) break;
+            total_launches += c->last_launches;
+            if (cudaMemcpyAsync(c->h_pts[ring], c->d_out.ptr, sizeof(ProofPoints) * B, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaEventRecord(c->ev_done[ring], st) != cudaSuccess) {
+                rc = G16_E_CUDA;
+                set_error(std::string("device pipeline: ") + cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+            trace("pipeline: chunk enqueued");
+            Pending cur;
+            cur.live = true; cur.first = first; cur.B = B; cur.off = off; cur.slot = (int)(g & 1); cur.ring = ring;
+            if ((rc = drain()) != G16_OK) break;   // the previous chunk: its bytes are written while this one runs
+            pend = cur;
+        }
+        if (rc != G16_OK && g + 1 < ngroups && fut.valid()) fut.wait();   // never leave the worker running on freed state
+    }
+    if (rc == G16_OK) rc = drain();
+    else if (fut.valid()) fut.wait();
+    if (rc != G16_OK) {
+        cudaStreamSynchronize(st);
+        return rc;
+    }
+    c->last_launches = total_launches;
+    c->ctx->last_launches = total_launches;
+    return G16_OK;
+}
+
+extern "C" {
+
+int g16_prove_wires(g16_circuit* c, size_t n, const uint8_t* wires_be, const uint8_t* rnd, uint8_t* proofs) {
+    if (!c || !wires_be || !proofs || n == 0) {
+        set_error("g16_prove_wires: bad arguments");
+        return G16_E_ARG;
+    }
+    G16_CUDA(cudaSetDevice(c->ctx->device));
+    G16_LOCK(c->ctx);
+    if (c->world > 1) return prove_wires_sync(c, n, wires_be, rnd, proofs);
+    const size_t SB = c->solve_batch;
+    auto launch = [&](size_t g) {
+        const size_t first = g * SB;
+        return std::async(std::launch::async, stage_wires, c, (int)(g & 1), std::min(SB, n - first),
+                          wires_be + first * c->nw * 32, rnd ? rnd + 96 * first : nullptr, first);
+    };
+    return run_pipeline(c, n, launch, proofs, [](size_t, size_t) {});
 }
 
 int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, size_t n_values, const uint8_t* rnd,
@@ -897,67 +1117,30 @@ int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, siz
                   "g16_prove_wires_dev collectively on every rank");
         return G16_E_ARG;
     }
-    cudaStream_t st = c->ctx->stream;
-    const size_t plen = c->has_commitment ? 388 : 324;
     // groups of solve_batch proofs are solved together (stage A); each group is proved in chunks of
     // max_batch (stage B) while the next group is being solved
     const size_t SB = c->solve_batch;
-    const size_t ngroups = (n + SB - 1) / SB;
-    auto group_size = [&](size_t g) { return std::min(SB, n - g * SB); };
     const bool solve_overlap = !(getenv("G16_SOLVE_OVERLAP") && atoi(getenv("G16_SOLVE_OVERLAP")) == 0);
     auto launch = [&](size_t g) {
-        size_t first = g * SB;
+        const size_t first = g * SB, G = std::min(SB, n - first);
         if (c->plan.valid)   // G16_SOLVE_OVERLAP=0 runs the device solver between groups instead of beside them
-            return std::async(solve_overlap ? std::launch::async : std::launch::deferred, stage_solve_gpu, c, (int)(g & 1),
-                              group_size(g), assignments_be + first * nin * 32, rnd ? rnd + 96 * first : nullptr, first);
-        return std::async(std::launch::async, stage_solve, c, (int)(g & 1), group_size(g), assignments_be + first * nin * 32,
+            return std::async(solve_overlap ? std::launch::async : std::launch::deferred, stage_solve_gpu, c, (int)(g & 1), G,
+                              assignments_be + first * nin * 32, rnd ? rnd + 96 * first : nullptr, first);
+        return std::async(std::launch::async, stage_solve, c, (int)(g & 1), G, assignments_be + first * nin * 32,
                           rnd ? rnd + 96 * first : nullptr, first, true);
     };
-    std::future<StageResult> fut = launch(0);
-    int total_launches = 0;
-    for (size_t g = 0; g < ngroups; g++) {
-        StageResult sr = fut.get();
-        if (sr.rc != G16_OK) {
-            set_error(sr.err);
-            return sr.rc;
-        }
-        if (g + 1 < ngroups) fut = launch(g + 1);   // solve group g+1 while the device proves group g
-        g16_circuit::Slot& sl = c->slots[g & 1];
-        const size_t G = group_size(g);
-        int rc = G16_OK;
-        if (cudaStreamWaitEvent(st, sl.ready, 0) != cudaSuccess) { rc = G16_E_CUDA; set_error("cudaStreamWaitEvent failed"); }
-        for (size_t off = 0; off < G && rc == G16_OK; off += c->max_batch) {
-            const size_t B = std::min(c->max_batch, G - off), first = g * SB + off;
-            std::vector<ProofPoints> pts(B);
-            if ((rc = prove_device(c, B, (const Fr*)sl.d_wires.ptr + off * c->wstride)) != G16_OK) break;
-            total_launches += c->last_launches;
-            if (cudaMemcpyAsync(pts.data(), c->d_out.ptr, sizeof(ProofPoints) * B, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-                cudaStreamSynchronize(st) != cudaSuccess) {
-                rc = G16_E_CUDA;
-                set_error(std::string("device pipeline: ") + cudaGetErrorString(cudaGetLastError()));
-                break;
+    return run_pipeline(c, n, launch, proofs, [&](size_t first, size_t B) {
+        if (!pws) return;
+        parallel_for(B, [&](size_t b) {
+            uint8_t* o = pws + pw_stride * (first + b);
+            const uint32_t hdr[3] = {(uint32_t)npub, 0, (uint32_t)npub};
+            for (int q = 0; q < 3; q++) {
+                o[4 * q] = hdr[q] >> 24; o[4 * q + 1] = hdr[q] >> 16; o[4 * q + 2] = hdr[q] >> 8; o[4 * q + 3] = hdr[q];
             }
-            for (size_t b = 0; b < B; b++) {
-                write_proof_bytes(pts[b], c->has_commitment ? &sl.commits[off + b] : nullptr, proofs + plen * (first + b));
-                if (pws) {
-                    uint8_t* o = pws + pw_stride * (first + b);
-                    uint32_t hdr[3] = {(uint32_t)npub, 0, (uint32_t)npub};
-                    for (int q = 0; q < 3; q++) {
-                        o[4 * q] = hdr[q] >> 24; o[4 * q + 1] = hdr[q] >> 16; o[4 * q + 2] = hdr[q] >> 8; o[4 * q + 3] = hdr[q];
-                    }
-                    for (size_t i = 0; i < npub; i++)   // public wires = the first npub assignment values, reduced mod r
-                        HFr::from_be(assignments_be + ((first + b) * nin + i) * 32).to_be(o + 12 + 32 * i);
-                }
-            }
-        }
-        if (rc != G16_OK) {
-            if (g + 1 < ngroups) fut.wait();   // never leave the worker running on freed state
-            return rc;
-        }
-    }
-    c->last_launches = total_launches;
-    c->ctx->last_launches = total_launches;
-    return G16_OK;
+            for (size_t i = 0; i < npub; i++)   // public wires = the first npub assignment values, reduced mod r
+                HFr::from_be(assignments_be + ((first + b) * nin + i) * 32).to_be(o + 12 + 32 * i);
+        });
+    });
 }
 
 int g16_prove(g16_circuit* c, const uint8_t* witness_gz, size_t witness_len, const uint8_t rnd[96], uint8_t* proof,

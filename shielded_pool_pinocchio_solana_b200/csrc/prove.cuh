@@ -73,11 +73,16 @@ struct g16_circuit {
     // k+1 into the other slot (its commitment MSM runs on `aux_stream` with its own MSM scratch).
     struct Slot {
         g16::DeviceBuf d_wires, d_commit_vals, d_commit_out, d_asg_be, d_rnd_be, d_err, d_chal;
+        g16::DeviceBuf d_wires_be;       // g16_prove_wires: the caller's big-endian wire vectors (grown on first use)
         void* h_stage = nullptr;         // pinned: assignments | rnd | challenges | err
         void* h_wires = nullptr;         // pinned, max_batch * wstride Fr
         cudaEvent_t ready = nullptr;     // wires of this slot are in d_wires
         std::vector<g16::G1Affine> commits;
     } slots[2];
+    // results of the proving chunks come back through two pinned buffers: the host serialises chunk k-1 while
+    // the device proves chunk k
+    g16::ProofPoints* h_pts[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};
     cudaStream_t aux_stream = nullptr;
     g16::MsmRunner<g16::Fp> g1_aux;
     g16::GpuSolverPlan plan;             // valid => witnesses are solved on the GPU

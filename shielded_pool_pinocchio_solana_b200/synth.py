@@ -27,6 +27,8 @@ H_COUNT = 2138922168
 H_INVZERO = 2534161455
 H_NBITS = 4115454955
 H_COMMIT = 4156202267
+MIX_RECENT = 0.575  # probability that an operand of a value_mix row is a recent wire
+MIX_SPAN = 8       # value_mix rows: how far back a 'recent' operand reaches (sets the dependency depth)
 HINT_NAMES = {
     H_DECOMPOSE: "github.com/consensys/gnark/std/rangecheck.DecomposeHint",
     H_RANDOMIZE: "github.com/consensys/gnark/internal/hints.Randomize",
@@ -124,7 +126,11 @@ class SyntheticCircuit:
 
 
 def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=48, seed=0xA0D17,
-          dens_b=5, frac_c2=0.31, n_coeffs=256, div_zero=False):
+          dens_b=5, frac_c2=0.31, n_coeffs=256, div_zero=False, value_mix=None):
+    """`value_mix` = (zero, one, small, uniform) fractions: body rows are then drawn from four kinds whose SOLVED
+    wire is a balanced bit (xor of two bits), a zero (b * (1 - b)), a byte (sum of 2^k * bit) or a uniform field
+    element, and the secret inputs past the first 8 are bits / bytes / uniform values in matching proportions --
+    the witness-like value distribution of SURVEY.md 8(d) arrived at through the solver, not injected."""
     rng = random.Random(seed)
     assert n_public >= 2 and n_secret >= 8
     coeffs = [0, 1, 2, R - 1, R - 2] + [rng.randrange(1, R) for _ in range(n_coeffs)]
@@ -246,6 +252,58 @@ def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=4
         known.append(new)
         return new
 
+    # ---- witness-like value mix: pools of wires whose solved value is a bit / zero / byte -----
+    sec_kind = {}
+    if value_mix is not None:
+        f_zero, f_one, f_small, f_uni = value_mix
+        f_bit = 2.0 * f_one                         # balanced bits: half of them are ones
+        f_z = max(0.0, f_zero - f_one)              # the zeros that are not just 0-valued bits
+        assert abs(f_bit + f_z + f_small + f_uni - 1.0) < 1e-9
+        pools = {"bit": [], "zero": [], "small": [], "uni": list(known)}
+        for i in range(8, n_secret):
+            u = rng.random()
+            kind = "bit" if u < f_bit + f_z else ("small" if u < f_bit + f_z + f_small else "uni")
+            sec_kind[i] = kind
+            if kind != "uni":
+                pools["uni"].remove(S(i))
+                pools[kind].append(S(i))
+        assert len(pools["bit"]) >= 16
+        known = pools["uni"]
+        uniform_row = add_body_row
+
+        def pool_pick(kind, span=4096):
+            # half of the operands are recent wires: the dependency depth (solver levels per row) then matches the
+            # withdraw circuit's (657 levels for 12,452 rows)
+            pl = pools[kind]
+            return pl[rng.randrange(max(0, len(pl) - span), len(pl))] if rng.random() < MIX_RECENT else pl[rng.randrange(len(pl))]
+
+        def add_body_row():                          # noqa: F811 -- replaces the uniform-only row generator
+            nonlocal next_wire
+            u = rng.random()
+            if not pools["zero"]:
+                kind = "zero"                        # the xor rows pad their B side with zero-valued wires
+            elif u < f_bit:
+                kind = "bit"
+            elif u < f_bit + f_z:
+                kind = "zero"
+            elif u < f_bit + f_z + f_small:
+                kind = "small"
+            else:
+                return uniform_row()                 # draws its operands from `known` = the uniform wires only
+            new = next_wire
+            next_wire += 1
+            pad = lambda k: [((rng.randrange(5, 5 + n_coeffs) if rng.random() < 0.69 else 1), pool_pick("zero")) for _ in range(k)]
+            if kind == "bit":        # 2a * (b + zeros) = a + b - new   (xor)
+                a, b = pool_pick("bit", MIX_SPAN), pool_pick("bit", MIX_SPAN)
+                add_r1c([(2, a)], [(1, b)] + pad(dens_b - 1), [(1, a), (1, b), (3, new)], defines=new)
+            elif kind == "zero":     # a * (1 - a) = new
+                a = pool_pick("bit", MIX_SPAN)
+                add_r1c([(1, a)], [(1, 0), (3, a)], [(1, new)], defines=new)
+            else:                    # 1 * sum 2^k b_k = new   (a byte)
+                add_r1c([ONE], [(pow2[k], pool_pick("bit", MIX_SPAN)) for k in range(8)], [(1, new)], defines=new)
+            pools[kind].append(new)
+            return new
+
     body_wires = []
     while len(body_wires) < n_rows_before_commit and rows_so_far() < n_rows_target:
         body_wires.append(add_body_row())
@@ -328,6 +386,11 @@ def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=4
     def assign(aseed):
         r2 = random.Random((seed << 20) ^ aseed)
         sec = [r2.randrange(1, R) for _ in range(n_secret)]
+        for i, kind in sec_kind.items():
+            if kind == "bit":
+                sec[i] = r2.randrange(2)
+            elif kind == "small":
+                sec[i] = r2.randrange(256)
         sec[2] = r2.randrange(1 << 12)
         pub = [r2.randrange(R) for _ in range(n_public)]
         pub[0] = sec[0] * sec[0] % R
@@ -339,7 +402,11 @@ def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=4
     return out
 
 
-def audit_like():
+def audit_like(uniform=False):
     """Stand-in for the missing audit circuit: ~26K constraints, 2 public inputs, 1 commitment
-    (/root/reference/README.md:49; rlwe_audit.vk has 4 K points = ONE + 2 public + commitment)."""
-    return build(26000, n_public=2, n_secret=2400, commitment=True, n_committed=490, seed=0xA0D17)
+    (/root/reference/README.md:49; rlwe_audit.vk has 4 K points = ONE + 2 public + commitment).
+    Default: the solved witness has the witness-like value mix of SURVEY.md 8(d) (40 % zero, 30 % one, 20 % < 2^8,
+    10 % uniform -- an RLWE audit circuit is range checks and small-coefficient arithmetic); `uniform=True` is the
+    round-1 variant whose every wire is a uniform field element (the worst case for the MSMs)."""
+    return build(26000, n_public=2, n_secret=2400, commitment=True, n_committed=490, seed=0xA0D17,
+                 value_mix=None if uniform else (0.4, 0.3, 0.2, 0.1))
