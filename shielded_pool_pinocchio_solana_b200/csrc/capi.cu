@@ -220,6 +220,7 @@ int g16_profile_read(g16_ctx* ctx, double ms[8], double launches[8], double unit
     if (!ctx || !ms || !launches || !units) return G16_E_ARG;
     G16_CUDA(cudaSetDevice(ctx->device));
     G16_LOCK(ctx);
+    ctx->prof.timeline_dump();
     ctx->prof.read(ms, launches, units);
     return G16_OK;
 }

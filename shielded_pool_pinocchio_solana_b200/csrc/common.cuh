@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -63,6 +64,35 @@ struct KernelProfiler {
         if (!enabled) return;
         cudaEventRecord(recs[used].b, st);
         used++;
+    }
+    // G16_TIMELINE=1: named events on whatever stream, dumped (ms since the first mark) by timeline_dump();
+    // unlike `enabled` this leaves the stream overlap of the pipeline untouched
+    struct Mark {
+        cudaEvent_t ev;
+        const char* a;
+        const char* b;
+    };
+    std::vector<Mark> marks;
+    bool timeline = getenv("G16_TIMELINE") && atoi(getenv("G16_TIMELINE")) != 0;
+    void mark(const char* a, const char* b, cudaStream_t st) {
+        if (!timeline) return;
+        Mark m;
+        cudaEventCreate(&m.ev);
+        m.a = a;
+        m.b = b;
+        cudaEventRecord(m.ev, st);
+        marks.push_back(m);
+    }
+    void timeline_dump() {
+        if (marks.empty()) return;
+        cudaDeviceSynchronize();
+        for (auto& m : marks) {
+            float t = 0;
+            cudaEventElapsedTime(&t, marks[0].ev, m.ev);
+            fprintf(stderr, "[timeline %8.3f ms] %s %s\n", t, m.a, m.b);
+        }
+        for (auto& m : marks) cudaEventDestroy(m.ev);
+        marks.clear();
     }
     // sums per tag (0..7): milliseconds, launches, units
     void read(double ms[8], double launches[8], double units[8]) {

@@ -4,13 +4,12 @@
 // gnark walks the instruction levels with goroutines; on a 16-core host that costs 10-20 ms per
 // audit-size proof and caps a box at a few hundred proofs/s -- less than ONE B200 proves.  Here the
 // level structure is compiled once per circuit into a static plan (which wire each row defines is
-// independent of the witness), and ONE WARP per proof executes it: lanes take the instructions of a
-// level (median ~20 per level in the reference circuit), __syncwarp() separates levels, wires live in
-// HBM in the layout the prover reads.  The solve is latency-bound (~10^3 dependent levels), so the
-// plan is flattened into per-level records (one 32-byte record per instruction, then its terms) to keep
-// the chain of dependent loads at record -> terms -> wires, the terms of a row are fetched four at a
-// time so their loads and products overlap, and eight proofs share a CTA so that the solver occupies
-// few SMs while the proving kernels of the previous group run beside it.
+// independent of the witness), and a CTA per proof executes it: four lanes share a row of a level
+// (median ~20 rows per level in the reference circuit), __syncthreads() separates levels, wires live in
+// HBM in the layout the prover reads.  The solve is latency-bound (~10^3 dependent levels of ~10 dependent
+// modmuls when one thread owns a row), so the plan is flattened into per-level records (one 32-byte record
+// per instruction) to keep the chain of dependent loads at record -> terms -> wires, and the terms of a row
+// are spread over lanes so that their loads and products run side by side (k_solve_tpi).
 // The BSB22 commitment splits the plan in two phases (prove.cu runs the commitment MSM between).
 // Circuits using a hint this file does not implement keep the host solver (solver.cpp).
 #include "gpusolver.cuh"
@@ -172,63 +171,81 @@ k_solve_levels(const uint32_t* __restrict__ lvl_off, const uint32_t* __restrict_
     }
 }
 
-// ---- warp-per-proof variant -------------------------------------------------------------------
-constexpr int SOLVE_WARPS = 8;   // proofs per CTA
+// ---- term-parallel variant (default) ------------------------------------------------------------------
+// A level is a handful of rows (median ~20), a row ~10 terms, a term one modmul of ~600 cycles latency: with
+// one thread per row the level costs the SUM of its terms' latencies.  Here SOLVE_TPI lanes share a row: each
+// takes every SOLVE_TPI-th term (descriptors, wires and coefficients of up to four terms are in flight
+// together), the partial sums of L, R and O meet through two xor-shuffles and the first lane finishes the row.
+constexpr int SOLVE_TPI = 4;
+constexpr int SOLVE_ROWS = SOLVE_THREADS / SOLVE_TPI;   // rows per pass of a CTA
+
+__device__ __forceinline__ Fr shfl_xor_fr(uint32_t mask, const Fr& a, int d) {
+    Fr r;
+#pragma unroll
+    for (int l = 0; l < 8; l++) r.v[l] = __shfl_xor_sync(mask, a.v[l], d);
+    return r;
+}
 
 // rec[2k]   = (mode, defined wire, coefficient id of the defined wire's term, constraint row)
 // rec[2k+1] = (calldata offset of the instruction, nL, nR, nO)          k = position in level order
-__global__ void __launch_bounds__(32 * SOLVE_WARPS)
-k_solve_warp(const uint32_t* __restrict__ lvl_off, const uint4* __restrict__ rec, const uint32_t* __restrict__ calldata,
-             const Fr* __restrict__ coeffs, const Fr* __restrict__ coeff_invs, Fr* wires, size_t wstride,
-             size_t blinder_slot, uint32_t nproofs, uint32_t lvl_begin, uint32_t lvl_end, int unit_ids, uint32_t* err) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t b = blockIdx.x * SOLVE_WARPS + (threadIdx.x >> 5);
-    if (b >= nproofs) return;   // whole warp
+__global__ void __launch_bounds__(SOLVE_THREADS)
+k_solve_tpi(const uint32_t* __restrict__ lvl_off, const uint4* __restrict__ rec, const uint32_t* __restrict__ calldata,
+            const Fr* __restrict__ coeffs, const Fr* __restrict__ coeff_invs, Fr* wires, size_t wstride,
+            size_t blinder_slot, uint32_t lvl_begin, uint32_t lvl_end, int unit_ids, uint32_t* err) {
+    const uint32_t b = blockIdx.x;
+    const uint32_t grp = threadIdx.x / SOLVE_TPI, sub = threadIdx.x % SOLVE_TPI;
+    const uint32_t gmask = ((1u << SOLVE_TPI) - 1u) << ((threadIdx.x & 31u) & ~(uint32_t)(SOLVE_TPI - 1));
     Fr* w = wires + (size_t)b * wstride;
     uint32_t* e = err + b;
     for (uint32_t lv = lvl_begin; lv < lvl_end; lv++) {
         const uint32_t s = lvl_off[lv], t = lvl_off[lv + 1];
-        for (uint32_t k = s + lane; k < t; k += 32) {
+        for (uint32_t k = s + grp; k < t; k += SOLVE_ROWS) {   // uniform over the SOLVE_TPI lanes of a row
             const uint4 inf = rec[2 * k], shp = rec[2 * k + 1];
             const uint32_t* cd = calldata + shp.x;
             if (inf.x >= 16) {
-                run_hint(inf.x - 16, cd, w, coeffs, unit_ids, w[blinder_slot], e);
+                if (sub == 0) run_hint(inf.x - 16, cd, w, coeffs, unit_ids, w[blinder_slot], e);
                 continue;
             }
             const uint32_t nl = shp.y, nlr = shp.y + shp.z, nt = nlr + shp.w;
             const uint32_t skip = inf.x == 0 ? NO_WIRE : inf.y;
             const uint32_t* terms = cd + 4;
             Fr L = Fr::zero(), Rr = Fr::zero(), O = Fr::zero();
-            for (uint32_t i0 = 0; i0 < nt; i0 += 4) {
+            for (uint32_t i0 = sub; i0 < nt; i0 += 4 * SOLVE_TPI) {
                 uint32_t cid[4], wid[4];
                 Fr x[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const bool in = i0 + j < nt;
-                    cid[j] = in ? terms[2 * (i0 + j)] : 0u;
-                    wid[j] = in ? terms[2 * (i0 + j) + 1] : skip;
+                    const uint32_t i = i0 + j * SOLVE_TPI;
+                    cid[j] = i < nt ? terms[2 * i] : 0u;
+                    wid[j] = i < nt ? terms[2 * i + 1] : skip;
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    // kind: 0 skip, 1 +x, 2 -x, 3 c*x, 4 +c (constant term)
                     x[j] = Fr::zero();
-                    if (i0 + j < nt && wid[j] != skip && wid[j] != CCS_CONST_WIRE) x[j] = w[wid[j]];
+                    if (i0 + j * SOLVE_TPI < nt && wid[j] != skip && wid[j] != CCS_CONST_WIRE) x[j] = w[wid[j]];
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    if (i0 + j >= nt || wid[j] == skip) continue;
+                    const uint32_t i = i0 + j * SOLVE_TPI;
+                    if (i >= nt || wid[j] == skip) continue;
                     Fr v;
                     if (wid[j] == CCS_CONST_WIRE) v = coeffs[cid[j]];
                     else if (unit_ids && cid[j] == 1) v = x[j];
                     else if (unit_ids && cid[j] == 3) v = x[j].neg();
                     else if (unit_ids && cid[j] == 0) continue;
                     else v = coeffs[cid[j]] * x[j];
-                    const uint32_t i = i0 + j;
                     if (i < nl) L = L + v;
                     else if (i < nlr) Rr = Rr + v;
                     else O = O + v;
                 }
             }
+#pragma unroll
+            for (int d = 1; d < SOLVE_TPI; d <<= 1) {
+                if (nl > 1) L = L + shfl_xor_fr(gmask, L, d);    // a single L term sits in lane 0 of the row
+                Rr = Rr + shfl_xor_fr(gmask, Rr, d);
+                O = O + shfl_xor_fr(gmask, O, d);
+            }
+            if (sub != 0) continue;
             if (inf.x == 0) {
                 if (L * Rr != O) atomicMin(e, inf.w + 1);           // constraint row (1-based)
             } else if (inf.x == 1) {
@@ -246,7 +263,7 @@ k_solve_warp(const uint32_t* __restrict__ lvl_off, const uint4* __restrict__ rec
                 } else w[inf.y] = (O * L.inverse() - Rr) * coeff_invs[inf.z];
             }
         }
-        __syncwarp();   // orders this level's wire stores before the next level's loads (same warp)
+        __syncthreads();
     }
 }
 
@@ -465,9 +482,8 @@ int GpuSolverPlan::run(const Fr* d_coeffs, int unit_ids, Fr* d_wires, size_t wst
                                                               d_coeff_invs, d_wires, wstride, nw + X_BLINDER, lvl_begin,
                                                               lvl_end, unit_ids, d_err);
     else
-        k_solve_warp<<<cdiv(B, SOLVE_WARPS), 32 * SOLVE_WARPS, 0, st>>>(d_lvl_off, d_rec, d_calldata, d_coeffs, d_coeff_invs,
-                                                                        d_wires, wstride, nw + X_BLINDER, (uint32_t)B,
-                                                                        lvl_begin, lvl_end, unit_ids, d_err);
+        k_solve_tpi<<<(unsigned)B, SOLVE_THREADS, 0, st>>>(d_lvl_off, d_rec, d_calldata, d_coeffs, d_coeff_invs, d_wires, wstride,
+                                                           nw + X_BLINDER, lvl_begin, lvl_end, unit_ids, d_err);
     G16_CUDA(cudaGetLastError());
     return G16_OK;
 }

@@ -2,27 +2,31 @@
 #include "msm.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace g16 {
 
 int msm_pick_window(size_t n, size_t batch) {
-    // Work per batch element in modular multiplications: ~6.5 per batched-affine bucket addition
-    // (n * W of them) plus ~30 per bucket for the running-sum reduction (one mixed + one full XYZZ
-    // addition).  The tree rounds parallelise over ENTRIES, not buckets, so a small MSM no longer
-    // needs a huge window "to fill the chip" (round 1 picked c = 18 for 2^14 points).
+    // Work per batch element in modular multiplications: 10 per bucket addition (XYZZ += affine, n * W of
+    // them for uniform scalars) plus the running-sum reduction, two full XYZZ additions (28) per bucket.  The
+    // reduction runs as short dependent chains on few threads and reaches ~40 % of the multiplier throughput
+    // the accumulation gets (profiles/r02_kernel_shares_device_step.csv), hence the weight of 70 -- and ties go
+    // to the SMALLER window: witness-like scalars (mostly 0 / 1 / bytes) produce far fewer entries than
+    // uniform ones, which moves their optimum further down.  G16_WINDOW_DELTA shifts the choice (experiments).
     (void)batch;
     int best = 8;
     double best_cost = 1e300;
     for (int c = 6; c <= 22; c++) {
         double W = ceil(254.0 / c);
         double nb = ldexp(1.0, c - 1);
-        double cost = 6.5 * (double)n * W + 30.0 * nb;
-        if (cost < best_cost) {
+        double cost = 10.0 * (double)n * W + 70.0 * nb;
+        if (cost < best_cost * 0.995) {
             best_cost = cost;
             best = c;
         }
     }
-    return best;
+    if (const char* e = getenv("G16_WINDOW_DELTA")) best += atoi(e);
+    return best < 4 ? 4 : (best > 22 ? 22 : best);
 }
 
 template <class F>
@@ -83,6 +87,9 @@ void MsmScratch::release() {
 template <class F>
 void MsmRunner<F>::release() {
     for (auto& x : s) x.release();
+    if (ev_sorted) cudaEventDestroy(ev_sorted);
+    if (ev_accumulated) cudaEventDestroy(ev_accumulated);
+    ev_sorted = ev_accumulated = nullptr;
 }
 
 namespace {
@@ -171,6 +178,7 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
 
     // ---- sort the signed digits by bucket ----------------------------------------------------------
     dim3 dgrid(cdiv(n, MSM_DIGIT_THREADS), (unsigned)batch);
+    if (prof) prof->mark(label, "begin", st);
     G16_CUDA(cudaMemsetAsync(counts, 0, 4 * nbuckets, st));
     G16_CUDA(cudaMemsetAsync(tab, 0, 4 * (2 * VB_CLASSES + 8), st));
     k_msm_digits<0><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery, cfg,
@@ -189,10 +197,26 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     k_vb_order<<<cdiv(nvmax, MSM_VB_THREADS), MSM_VB_THREADS, 0, st>>>(vb_size, vbase + nbuckets, first, cursor, order);
     launches += 12;
     // ---- bucket accumulation ---------------------------------------------------------------------------
-    if (prof) prof->begin(sizeof(F) == sizeof(Fp) ? PROF_MSM_ACC_G1 : PROF_MSM_ACC_G2, (double)batch * n, st);
-    k_msm_accumulate<F><<<cdiv(nvmax, 128), 128, 0, st>>>(bases.table, entries, vb_start, vb_size, order, vbase + nbuckets,
+    if (prof) prof->mark(label, "sorted", st);
+    cudaStream_t sa = st;
+    if (acc_stream && acc_stream != st && !(prof && prof->enabled)) {
+        if (!ev_sorted) {
+            G16_CUDA(cudaEventCreateWithFlags(&ev_sorted, cudaEventDisableTiming));
+            G16_CUDA(cudaEventCreateWithFlags(&ev_accumulated, cudaEventDisableTiming));
+        }
+        sa = acc_stream;
+        G16_CUDA(cudaEventRecord(ev_sorted, st));
+        G16_CUDA(cudaStreamWaitEvent(sa, ev_sorted, 0));
+    }
+    if (prof) prof->begin(sizeof(F) == sizeof(Fp) ? PROF_MSM_ACC_G1 : PROF_MSM_ACC_G2, (double)batch * n, sa);
+    k_msm_accumulate<F><<<cdiv(nvmax, 128), 128, 0, sa>>>(bases.table, entries, vb_start, vb_size, order, vbase + nbuckets,
                                                           result_vb);
-    if (prof) prof->end(st);
+    if (prof) prof->end(sa);
+    if (sa != st) {
+        G16_CUDA(cudaEventRecord(ev_accumulated, sa));
+        G16_CUDA(cudaStreamWaitEvent(st, ev_accumulated, 0));
+    }
+    if (prof) prof->mark(label, "accumulated", st);
     {
         const unsigned jw = (unsigned)(cdiv(hot_cap, MSM_JOIN_THREADS / 32) < (unsigned)SM_COUNT * 8 ? cdiv(hot_cap, MSM_JOIN_THREADS / 32)
                                                                                                  : SM_COUNT * 8);
@@ -206,6 +230,7 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     k_msm_reduce2<F><<<(unsigned)(batch * parts), MSM_R2_THREADS, 0, st>>>(seg_acc, seg_run, nseg, parts, per, part_out);
     k_msm_reduce3<F><<<(unsigned)batch, 32, 0, st>>>(part_out, parts, seg, d_out);
     launches += 3;
+    if (prof) prof->mark(label, "reduced", st);
     G16_CUDA(cudaGetLastError());
     return G16_OK;
 }

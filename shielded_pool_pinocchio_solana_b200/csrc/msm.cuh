@@ -553,11 +553,18 @@ class MsmRunner {
     // kernels launched by the last run() (for bench.py's gpu_launches)
     int launches = 0;
     KernelProfiler* prof = nullptr;   // optional: times the accumulate kernel
+    const char* label = "msm";        // name in the G16_TIMELINE dump
+    // Optional: the bucket accumulation (the one throughput-bound kernel; its grid fills every SM's register file
+    // for milliseconds) is launched on this LOW-priority stream, so that the short latency-bound kernels of the
+    // other MSMs running beside it (scans, ordering, bucket reduction: high-priority `st`) get the CTA slots
+    // that free up instead of queueing behind the whole grid.
+    cudaStream_t acc_stream = nullptr;
 
    private:
     enum { S_COUNTS, S_STARTS, S_TILES, S_ENTRIES, S_NV, S_VBASE, S_VBSTART, S_VBSIZE, S_ORDER, S_TABLES, S_HOT,
            S_RESULT, S_SEGACC, S_SEGRUN, S_PARTS, S_COUNT };
     MsmScratch s[S_COUNT];
+    cudaEvent_t ev_sorted = nullptr, ev_accumulated = nullptr;
 };
 
 }  // namespace g16

@@ -224,28 +224,34 @@ __device__ G1XYZZ g1_scalar_mul(const G1Affine& p, const Fr& k) {
     return acc;
 }
 
-// One 32-thread CTA per proof: lanes 0/1 compute s*Ar and r*Bs1, lane 0 assembles Krs; lanes 0..3
-// convert the four outputs out of Montgomery form.
-__global__ void __launch_bounds__(32)
-k_finalize(const G1Affine* __restrict__ ar, const G1Affine* __restrict__ bs1, const G2Affine* __restrict__ bs2,
-           const G1Affine* __restrict__ kz, const G1Affine* __restrict__ pok, const Fr* __restrict__ wires,
-           size_t wstride, size_t nw, ProofPoints* __restrict__ out) {
-    __shared__ G1XYZZ part[2];
-    uint32_t b = blockIdx.x, t = threadIdx.x;
+// The two 254-bit scalar multiplications of the Krs assembly, s*Ar and r*Bs1: ~3.5 K dependent modmuls each
+// (1.2 ms).  One 64-thread CTA per proof, one scalar per warp (no divergence between the two ladders).  Runs on
+// the side stream right behind the A and B1 MSMs, i.e. under the quotient and the K|Z MSM of the main stream.
+__global__ void __launch_bounds__(64)
+k_scalar_muls(const G1Affine* __restrict__ ar, const G1Affine* __restrict__ bs1, const Fr* __restrict__ wires,
+              size_t wstride, size_t nw, uint32_t stride_b, G1XYZZ* __restrict__ parts) {
+    const uint32_t b = blockIdx.x, which = threadIdx.x >> 5;
+    if (threadIdx.x & 31) return;
     const Fr* x = wires + (size_t)b * wstride + nw;
-    if (t < 2) {
-        Fr k = (t == 0 ? x[X_S] : x[X_R]).from_mont();
-        part[t] = g1_scalar_mul(t == 0 ? ar[b] : bs1[b], k);
-    }
-    __syncthreads();
+    const Fr k = (which == 0 ? x[X_S] : x[X_R]).from_mont();
+    parts[(size_t)which * stride_b + b] = g1_scalar_mul(which == 0 ? ar[b] : bs1[b], k);
+}
+
+// One 32-thread CTA per proof: lane 0 assembles Krs = s*Ar + r*Bs1 + (K|Z sum); lanes 0..3 convert the four
+// outputs out of Montgomery form.
+__global__ void __launch_bounds__(32)
+k_finalize(const G1Affine* __restrict__ ar, const G1XYZZ* __restrict__ parts, uint32_t stride_b,
+           const G2Affine* __restrict__ bs2, const G1Affine* __restrict__ kz, const G1Affine* __restrict__ pok,
+           ProofPoints* __restrict__ out) {
+    uint32_t b = blockIdx.x, t = threadIdx.x;
     auto unmont1 = [](G1Affine p) {
         p.x = p.x.from_mont();
         p.y = p.y.from_mont();
         return p;
     };
     if (t == 0) {
-        G1XYZZ acc = part[0];
-        acc.add(part[1]);
+        G1XYZZ acc = parts[b];
+        acc.add(parts[(size_t)stride_b + b]);
         acc.madd(kz[b]);
         out[b].krs = unmont1(acc.to_affine());
     } else if (t == 1) {
@@ -271,7 +277,7 @@ g16_circuit::~g16_circuit() {
     }
     cudaFree(d_coeffs);
     cudaFree(d_mapA); cudaFree(d_mapB); cudaFree(d_mapKZ); cudaFree(d_mapPok);
-    cudaFree(d_tmp_g1); cudaFree(d_tmp_g2);
+    cudaFree(d_tmp_g1); cudaFree(d_tmp_g2); cudaFree(d_parts);
     cudaFree(d_map_commit);
     for (auto& sl : slots) {
         if (sl.h_stage) cudaFreeHost(sl.h_stage);
@@ -283,14 +289,16 @@ g16_circuit::~g16_circuit() {
         if (ev_done[i]) cudaEventDestroy(ev_done[i]);
     }
     g1_aux.release();
-    g1_side.release();
+    for (auto& r : g1_side) r.release();
     g2_side.release();
     if (aux_stream) cudaStreamDestroy(aux_stream);
-    for (int i = 0; i < 2; i++) {
+    if (acc_stream) cudaStreamDestroy(acc_stream);
+    for (int i = 0; i < N_SIDE; i++) {
         if (side[i]) cudaStreamDestroy(side[i]);
         if (ev_join[i]) cudaEventDestroy(ev_join[i]);
     }
     if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_h) cudaEventDestroy(ev_h);
 }
 
 namespace {
@@ -363,16 +371,18 @@ int prove_device(g16_circuit* c, size_t B, const Fr* W) {
     int launches = 0;
     if (!ctx->prof.enabled) {   // side streams start once the wires are in place
         G16_CUDA(cudaEventRecord(c->ev_fork, st));
-        G16_CUDA(cudaStreamWaitEvent(c->side[0], c->ev_fork, 0));
-        G16_CUDA(cudaStreamWaitEvent(c->side[1], c->ev_fork, 0));
+        for (int i = 0; i < g16_circuit::SIDE_SM; i++) G16_CUDA(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
     }
+    ctx->prof.mark("chunk", "begin", st);
     dim3 grid(cdiv(c->n, 256), 3, (unsigned)B);
     k_r1cs_spmv<<<grid, 256, 0, st>>>(c->d_rowptr[0], c->d_cid[0], c->d_wid[0], c->d_rowptr[1], c->d_cid[1],
                                       c->d_wid[1], c->d_rowptr[2], c->d_cid[2], c->d_wid[2], c->d_coeffs, W,
                                       c->wstride, abc, c->circ.nb_constraints, (uint32_t)c->n, c->unit_ids);
     launches++;
     ctx->ntt.launches = 0;
+    ctx->prof.mark("spmv", "done", st);
     G16_TRY(ctx->ntt.compute_h(abc, c->logn, B, st));
+    ctx->prof.mark("quotient", "done", st);
     launches += ctx->ntt.launches;
     G1Affine* rA = c->d_tmp_g1;
     G1Affine* rB1 = c->d_tmp_g1 + c->max_batch;
@@ -380,35 +390,77 @@ int prove_device(g16_circuit* c, size_t B, const Fr* W) {
     G1Affine* rPok = c->d_tmp_g1 + 3 * c->max_batch;
     // per-kernel profiling wants serial, un-overlapped launches
     const bool overlap = !ctx->prof.enabled;
-    cudaStream_t s1 = overlap ? c->side[0] : st, s2 = overlap ? c->side[1] : st;
-    c->g1_side.prof = c->g2_side.prof = &ctx->prof;
-    G16_TRY(c->g1_side.run(c->bA, W, c->wstride, c->d_mapA, 1, B, rA, s1));
-    launches += c->g1_side.launches;
-    G16_TRY(c->g1_side.run(c->bB1, W, c->wstride, c->d_mapB, 1, B, rB1, s1));
-    launches += c->g1_side.launches;
-    if (c->has_commitment) {
-        G16_TRY(c->g1_side.run(c->bPok, W, c->wstride, c->d_mapPok, 1, B, rPok, s1));
-        launches += c->g1_side.launches;
-    } else {
-        G16_CUDA(cudaMemsetAsync(rPok, 0, sizeof(G1Affine) * B, s1));
+    auto on = [&](int i) { return overlap ? c->side[i] : st; };
+    cudaStream_t sA = on(g16_circuit::SIDE_A), sB1 = on(g16_circuit::SIDE_B1), sPok = on(g16_circuit::SIDE_POK),
+                 sB2 = on(g16_circuit::SIDE_B2), sSm = on(g16_circuit::SIDE_SM);
+    const bool low_acc = overlap && !(getenv("G16_ACC_STREAM") && atoi(getenv("G16_ACC_STREAM")) == 0);
+    for (auto& r : c->g1_side) {
+        r.prof = &ctx->prof;
+        r.acc_stream = low_acc ? c->acc_stream : nullptr;
     }
-    G16_TRY(c->g2_side.run(c->bB2, W, c->wstride, c->d_mapB, 1, B, c->d_tmp_g2, s2));
+    c->g2_side.prof = &ctx->prof;
+    c->g2_side.acc_stream = low_acc ? c->acc_stream : nullptr;
+    c->g1_side[0].label = "A";
+    c->g1_side[1].label = "B1";
+    c->g1_side[2].label = "PoK";
+    c->g2_side.label = "B2";
+    ctx->g1.label = "KZ";
+    G16_TRY(c->g2_side.run(c->bB2, W, c->wstride, c->d_mapB, 1, B, c->d_tmp_g2, sB2));   // the longest side chain first
     launches += c->g2_side.launches;
-    G16_TRY(ctx->g1.run(c->bKZ, W, c->wstride, c->d_mapKZ, 1, B, rKZ, st, abc, 3 * c->n));
+    G16_TRY(c->g1_side[0].run(c->bA, W, c->wstride, c->d_mapA, 1, B, rA, sA));
+    launches += c->g1_side[0].launches;
+    G16_TRY(c->g1_side[1].run(c->bB1, W, c->wstride, c->d_mapB, 1, B, rB1, sB1));
+    launches += c->g1_side[1].launches;
+    const bool split = ctx->world > 1;   // partial sums until the all-gather: the scalar multiplications wait for it
+    if (!split) {
+        if (overlap) {
+            G16_CUDA(cudaEventRecord(c->ev_join[g16_circuit::SIDE_A], sA));
+            G16_CUDA(cudaEventRecord(c->ev_join[g16_circuit::SIDE_B1], sB1));
+            G16_CUDA(cudaStreamWaitEvent(sSm, c->ev_join[g16_circuit::SIDE_A], 0));
+            G16_CUDA(cudaStreamWaitEvent(sSm, c->ev_join[g16_circuit::SIDE_B1], 0));
+        }
+        k_scalar_muls<<<(unsigned)B, 64, 0, sSm>>>(rA, rB1, W, c->wstride, c->nw, (uint32_t)c->max_batch, c->d_parts);
+        ctx->prof.mark("scalar_muls", "done", sSm);
+        launches++;
+    }
+    if (c->has_commitment) {
+        G16_TRY(c->g1_side[2].run(c->bPok, W, c->wstride, c->d_mapPok, 1, B, rPok, sPok));
+        launches += c->g1_side[2].launches;
+    } else {
+        G16_CUDA(cudaMemsetAsync(rPok, 0, sizeof(G1Affine) * B, sPok));
+    }
+    cudaStream_t sKZ = on(g16_circuit::SIDE_KZ);
+    if (overlap) {   // the quotient is ready: K|Z leaves the (low-priority) context stream too
+        G16_CUDA(cudaEventRecord(c->ev_h, st));
+        G16_CUDA(cudaStreamWaitEvent(sKZ, c->ev_h, 0));
+    }
+    ctx->g1.acc_stream = low_acc ? c->acc_stream : nullptr;
+    G16_TRY(ctx->g1.run(c->bKZ, W, c->wstride, c->d_mapKZ, 1, B, rKZ, sKZ, abc, 3 * c->n));
+    ctx->g1.acc_stream = nullptr;
     launches += ctx->g1.launches;
     if (overlap) {
-        G16_CUDA(cudaEventRecord(c->ev_join[0], s1));
-        G16_CUDA(cudaEventRecord(c->ev_join[1], s2));
-        G16_CUDA(cudaStreamWaitEvent(st, c->ev_join[0], 0));
-        G16_CUDA(cudaStreamWaitEvent(st, c->ev_join[1], 0));
+        // A and B1 are joined through SIDE_SM (which waited for both) unless the circuit is split across ranks
+        const int first = split ? g16_circuit::SIDE_A : g16_circuit::SIDE_POK;
+        if (split) {
+            G16_CUDA(cudaEventRecord(c->ev_join[g16_circuit::SIDE_A], sA));
+            G16_CUDA(cudaEventRecord(c->ev_join[g16_circuit::SIDE_B1], sB1));
+        }
+        G16_CUDA(cudaEventRecord(c->ev_join[g16_circuit::SIDE_POK], sPok));
+        G16_CUDA(cudaEventRecord(c->ev_join[g16_circuit::SIDE_B2], sB2));
+        if (!split) G16_CUDA(cudaEventRecord(c->ev_join[g16_circuit::SIDE_SM], sSm));
+        G16_CUDA(cudaEventRecord(c->ev_join[g16_circuit::SIDE_KZ], sKZ));
+        for (int i = first; i < g16_circuit::N_SIDE; i++)
+            if (!(split && i == g16_circuit::SIDE_SM)) G16_CUDA(cudaStreamWaitEvent(st, c->ev_join[i], 0));
     }
     if (ctx->world > 1) {   // partial sums of this rank's point ranges -> sums over all ranks (tiny NCCL all-gather)
         G16_TRY(comm_sum_points<Fp>(ctx, c->d_tmp_g1, 4 * c->max_batch, st));
         G16_TRY(comm_sum_points<Fp2>(ctx, c->d_tmp_g2, c->max_batch, st));
-        launches += 2;
+        k_scalar_muls<<<(unsigned)B, 64, 0, st>>>(rA, rB1, W, c->wstride, c->nw, (uint32_t)c->max_batch, c->d_parts);
+        launches += 3;
     }
-    k_finalize<<<(unsigned)B, 32, 0, st>>>(rA, rB1, c->d_tmp_g2, rKZ, rPok, W, c->wstride, c->nw,
+    k_finalize<<<(unsigned)B, 32, 0, st>>>(rA, c->d_parts, (uint32_t)c->max_batch, c->d_tmp_g2, rKZ, rPok,
                                            (ProofPoints*)c->d_out.ptr);
+    ctx->prof.mark("finalize", "done", st);
     launches++;
     G16_CUDA(cudaGetLastError());
     c->last_launches = launches;
@@ -591,11 +643,19 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
         G16_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         G16_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
     }
-    for (int i = 0; i < 2; i++) {
-        G16_CUDA(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        G16_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        G16_CUDA(cudaStreamCreateWithPriority(&c->acc_stream, cudaStreamNonBlocking, lo));
+    }
+    for (int i = 0; i < g16_circuit::N_SIDE; i++) {
+        int lo = 0, hi = 0;
+        G16_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // numerically lower = more urgent
+        G16_CUDA(cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, hi < lo ? hi + 1 : hi));
         G16_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
     G16_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    G16_CUDA(cudaEventCreateWithFlags(&c->ev_h, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         G16_CUDA(cudaMallocHost((void**)&c->h_pts[i], sizeof(ProofPoints) * max_batch));
         G16_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
@@ -621,6 +681,7 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
     }
     G16_CUDA(cudaMalloc(&c->d_tmp_g1, sizeof(G1Affine) * 4 * max_batch));
     G16_CUDA(cudaMalloc(&c->d_tmp_g2, sizeof(G2Affine) * max_batch));
+    G16_CUDA(cudaMalloc(&c->d_parts, sizeof(G1XYZZ) * 2 * max_batch));
     G16_CUDA(cudaMemsetAsync(c->d_tmp_g1, 0, sizeof(G1Affine) * 4 * max_batch, st));   // unused slots = infinity
     G16_CUDA(cudaMemsetAsync(c->d_tmp_g2, 0, sizeof(G2Affine) * max_batch, st));
     const NttDomain* dom;

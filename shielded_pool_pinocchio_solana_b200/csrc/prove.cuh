@@ -69,6 +69,7 @@ struct g16_circuit {
     g16::DeviceBuf d_abc, d_out;
     g16::G1Affine* d_tmp_g1 = nullptr;   // [4][max_batch]: A, B1, KZ, PoK results (Montgomery)
     g16::G2Affine* d_tmp_g2 = nullptr;   // [max_batch]
+    g16::G1XYZZ* d_parts = nullptr;      // [2][max_batch]: s*Ar, r*Bs1
     // Two pipeline slots: while the device proves chunk k out of slot k%2, the host solves chunk
     // k+1 into the other slot (its commitment MSM runs on `aux_stream` with its own MSM scratch).
     struct Slot {
@@ -88,13 +89,17 @@ struct g16_circuit {
     g16::GpuSolverPlan plan;             // valid => witnesses are solved on the GPU
     std::string host_solver_reason;
     uint32_t* d_map_commit = nullptr;    // committed wire ids (scalar map of the commitment MSM)
-    // The MSMs that only need the wires (A, B1, PoK on side[0]; B2 on side[1]) run on side streams
-    // next to SpMV -> H -> K|Z on the context stream: the latency-bound tails of one MSM (scan,
-    // ordering, bucket reduction) hide under another MSM's accumulation.
-    cudaStream_t side[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-    g16::MsmRunner<g16::Fp> g1_side;
+    // The MSMs that only need the wires (A, B1, PoK, B2) run on one side stream EACH next to
+    // SpMV -> H -> K|Z on the context stream, and the two scalar multiplications of the Krs assembly on a
+    // fifth one behind A and B1: every MSM ends in latency-bound kernels (scan, ordering, bucket reduction,
+    // ~1-3 ms of dependent point additions on few threads) that only cost time when nothing runs beside them.
+    // The side streams have a higher priority than the stream all bucket accumulations go to (acc_stream).
+    enum { SIDE_A = 0, SIDE_B1 = 1, SIDE_POK = 2, SIDE_B2 = 3, SIDE_SM = 4, SIDE_KZ = 5, N_SIDE = 6 };
+    cudaStream_t side[N_SIDE] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_h = nullptr, ev_join[N_SIDE] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    g16::MsmRunner<g16::Fp> g1_side[3];   // A, B1, PoK (own scratch each: they run concurrently)
     g16::MsmRunner<g16::Fp2> g2_side;
+    cudaStream_t acc_stream = nullptr;    // low priority: every bucket accumulation of this circuit (MsmRunner::acc_stream)
     int last_launches = 0;
     ~g16_circuit();
 };
