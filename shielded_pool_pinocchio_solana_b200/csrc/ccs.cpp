@@ -255,6 +255,9 @@ HintKind classify_hint(const std::string& name) {
     if (ends_with("std/internal/logderivarg.countHint")) return HINT_COUNT;
     if (ends_with("internal/hints.Randomize")) return HINT_RANDOMIZE;
     if (ends_with("frontend/cs.Bsb22CommitmentComputePlaceholder")) return HINT_COMMIT;
+    if (ends_with("std/math/emulated.mulHint")) return HINT_EMULATED_MUL;
+    if (ends_with("sw-grumpkin.decomposeScalar")) return HINT_GRUMPKIN_SPLIT;
+    if (ends_with("sw-grumpkin.decompose")) return HINT_GRUMPKIN_LIMBS;
     return HINT_UNKNOWN;
 }
 

@@ -33,6 +33,9 @@ enum HintKind {
     HINT_COUNT,
     HINT_RANDOMIZE,
     HINT_COMMIT,
+    HINT_EMULATED_MUL,        // gnark std/math/emulated.mulHint
+    HINT_GRUMPKIN_SPLIT,      // sunspot sw-grumpkin.decomposeScalar
+    HINT_GRUMPKIN_LIMBS,      // sunspot sw-grumpkin.decompose
 };
 
 struct Circuit {

@@ -126,8 +126,13 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     // so only the hot buckets of a skewed scalar vector are cut, into pieces that cost what a normal
     // bucket costs.
     const double mean = (double)bases.n * cfg.W / cfg.nb;
+    static const int ba_env = getenv("G16_MSM_BA") ? atoi(getenv("G16_MSM_BA")) : 0;
+    static const int ba_cap = getenv("G16_BA_CAP") ? atoi(getenv("G16_BA_CAP")) : 16;
+    const bool use_ba = ba_env != 0;
     uint32_t cap = 63;
     while (cap < VB_MAX_CAP && cap < 2.0 * mean) cap = 2 * cap + 1;
+    // batched-affine chains are short: BA_K of them per thread have to add up to enough threads to fill the chip
+    if (use_ba) cap = (uint32_t)(ba_cap < 2 ? 2 : (ba_cap > VB_MAX_CAP ? VB_MAX_CAP : ba_cap));
     const size_t nvmax = nbuckets + nentries / cap + 1;
     const size_t hot_cap = nentries / cap + 1;
     // ---- bucket reduction shape ----------------------------------------------------------------
@@ -156,6 +161,15 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     G16_TRY(s[S_SEGACC].ensure(sizeof(XYZZ<F>) * nseg_total));
     G16_TRY(s[S_SEGRUN].ensure(sizeof(XYZZ<F>) * nseg_total));
     G16_TRY(s[S_PARTS].ensure(sizeof(XYZZ<F>) * 2 * batch * parts));
+    const uint32_t ba_lanes = cdiv(nvmax, BA_K);
+    if (use_ba) {
+        const size_t slots = (size_t)ba_lanes * BA_K;
+        G16_TRY(s[S_BA_X].ensure(sizeof(F) * slots));
+        G16_TRY(s[S_BA_Y].ensure(sizeof(F) * slots));
+        G16_TRY(s[S_BA_PREFIX].ensure(sizeof(F) * slots));
+        G16_TRY(s[S_BA_CS].ensure(4 * slots));
+        G16_TRY(s[S_BA_CM].ensure(4 * slots));
+    }
     uint32_t* counts = (uint32_t*)s[S_COUNTS].ptr;   // doubles as the scatter cursor
     uint32_t* starts = (uint32_t*)s[S_STARTS].ptr;
     uint32_t* tiles = (uint32_t*)s[S_TILES].ptr;
@@ -209,8 +223,13 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
         G16_CUDA(cudaStreamWaitEvent(sa, ev_sorted, 0));
     }
     if (prof) prof->begin(sizeof(F) == sizeof(Fp) ? PROF_MSM_ACC_G1 : PROF_MSM_ACC_G2, (double)batch * n, sa);
-    k_msm_accumulate<F><<<cdiv(nvmax, 128), 128, 0, sa>>>(bases.table, entries, vb_start, vb_size, order, vbase + nbuckets,
-                                                          result_vb);
+    if (use_ba)
+        k_msm_accumulate_ba<F><<<cdiv(ba_lanes, BA_THREADS), BA_THREADS, 0, sa>>>(
+            bases.table, entries, vb_start, vb_size, order, vbase + nbuckets, ba_lanes, (F*)s[S_BA_X].ptr, (F*)s[S_BA_Y].ptr,
+            (F*)s[S_BA_PREFIX].ptr, (uint32_t*)s[S_BA_CS].ptr, (uint32_t*)s[S_BA_CM].ptr, result_vb);
+    else
+        k_msm_accumulate<F><<<cdiv(nvmax, 128), 128, 0, sa>>>(bases.table, entries, vb_start, vb_size, order,
+                                                              vbase + nbuckets, result_vb);
     if (prof) prof->end(sa);
     if (sa != st) {
         G16_CUDA(cudaEventRecord(ev_accumulated, sa));

@@ -329,6 +329,108 @@ k_msm_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict
     result_vb[v] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// batched-affine bucket accumulation
+// ---------------------------------------------------------------------------------------------
+// The chain kernel above pays 10 modmul per addition because its accumulator is projective.  Here a thread
+// owns BA_K virtual buckets (consecutive in the size-sorted order, so equally long) and advances all of them
+// one entry per step in AFFINE coordinates: the BA_K slopes of a step share one field inversion (Montgomery's
+// trick, 3 modmul per element) and an addition costs 6 modmul.  The inversion is a binary GCD on the ALU pipe
+// (no multiplier), so it runs beside the IMAD.WIDE work of the other warps of the SM.
+//   pass 1 (k up)  : d_k = x_P - x_acc;  prefix_k = d_0 ... d_(k-1)   (only the x coordinates are read)
+//   inversion      : inv = (d_0 ... d_(K-1))^-1
+//   pass 2 (k down): 1/d_k = inv * prefix_k;  inv *= d_k;  lambda = (y_P - y_acc)/d_k;  x3, y3
+// Per-thread state (accumulators, prefixes, chain descriptors) lives in global memory in [k][thread] order:
+// every access is coalesced across the warp; the points themselves are gathered from the table twice (the
+// second gather finds a window-table of a proving key in L2).  Exceptional steps (an operand at infinity,
+// equal or opposite x, an x coordinate of zero) are left out of the batch and done by the complete XYZZ
+// formulas with their own inversion: never taken on real inputs, exercised by the golden vectors.
+constexpr int BA_K = 64;
+constexpr int BA_THREADS = 128;
+
+template <class F>
+__device__ __noinline__ Affine<F> ba_slow_add(const Affine<F>& a, const Affine<F>& p) {
+    XYZZ<F> t = XYZZ<F>::from_affine(a);
+    t.madd(p);
+    return t.to_affine();
+}
+
+template <class F>
+__global__ void __launch_bounds__(BA_THREADS)
+k_msm_accumulate_ba(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ entries,
+                    const uint32_t* __restrict__ vb_start, const uint32_t* __restrict__ vb_size,
+                    const uint32_t* __restrict__ order, const uint32_t* __restrict__ nv_total, uint32_t nlanes,
+                    F* __restrict__ accx, F* __restrict__ accy, F* __restrict__ prefix, uint32_t* __restrict__ cs,
+                    uint32_t* __restrict__ cm, XYZZ<F>* __restrict__ result_vb) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nv = *nv_total;
+    const uint32_t q0 = t * BA_K;
+    if (t >= nlanes || q0 >= nv) return;
+    const uint32_t kn = min((uint32_t)BA_K, nv - q0);
+    // ---- step 0: every chain starts at its first entry --------------------------------------------
+    uint32_t steps = 0;
+    for (uint32_t k = 0; k < kn; k++) {
+        const uint32_t v = order[q0 + k];
+        const uint32_t s = vb_start[v], m = vb_size[v];
+        const size_t o = (size_t)k * nlanes + t;
+        cs[o] = s;
+        cm[o] = m;
+        steps = max(steps, m);
+        const uint32_t en = entries[s];
+        Affine<F> p = table[en & 0x7fffffffu];
+        if (en >> 31) p.y = p.y.neg();
+        accx[o] = p.x;
+        accy[o] = p.y;
+    }
+    // ---- steps 1 .. longest chain - 1 ----------------------------------------------------------------
+    for (uint32_t j = 1; j < steps; j++) {
+        F run = F::one();
+        bool any = false;
+        for (uint32_t k = 0; k < kn; k++) {
+            const size_t o = (size_t)k * nlanes + t;
+            if (j >= cm[o]) continue;
+            const uint32_t en = entries[cs[o] + j];
+            const F px = table[en & 0x7fffffffu].x;
+            const F ax = accx[o];
+            const F d = px - ax;
+            if (d.is_zero() || ax.is_zero() || px.is_zero()) continue;   // exceptional: handled in pass 2
+            prefix[o] = run;
+            run = run * d;
+            any = true;
+        }
+        F inv = any ? run.inverse() : run;
+        for (int k = (int)kn - 1; k >= 0; k--) {
+            const size_t o = (size_t)k * nlanes + t;
+            if (j >= cm[o]) continue;
+            const uint32_t en = entries[cs[o] + j];
+            Affine<F> p = table[en & 0x7fffffffu];
+            if (en >> 31) p.y = p.y.neg();
+            const F ax = accx[o], ay = accy[o];
+            const F d = p.x - ax;
+            if (d.is_zero() || ax.is_zero() || p.x.is_zero()) {
+                Affine<F> a = {ax, ay};
+                a = ba_slow_add(a, p);
+                accx[o] = a.x;
+                accy[o] = a.y;
+                continue;
+            }
+            const F dinv = inv * prefix[o];
+            inv = inv * d;
+            const F lam = (p.y - ay) * dinv;
+            const F x3 = lam.sqr() - ax - p.x;
+            const F y3 = lam * (ax - x3) - ay;
+            accx[o] = x3;
+            accy[o] = y3;
+        }
+    }
+    // ---- results (XYZZ with ZZ = ZZZ = 1, what the join / reduction kernels read) ---------------------------------
+    for (uint32_t k = 0; k < kn; k++) {
+        const size_t o = (size_t)k * nlanes + t;
+        Affine<F> a = {accx[o], accy[o]};
+        result_vb[order[q0 + k]] = XYZZ<F>::from_affine(a);
+    }
+}
+
 template <class P>
 __device__ __forceinline__ P shfl_down_point(const P& p, int delta) {
     P r;
@@ -562,7 +664,7 @@ class MsmRunner {
 
    private:
     enum { S_COUNTS, S_STARTS, S_TILES, S_ENTRIES, S_NV, S_VBASE, S_VBSTART, S_VBSIZE, S_ORDER, S_TABLES, S_HOT,
-           S_RESULT, S_SEGACC, S_SEGRUN, S_PARTS, S_COUNT };
+           S_RESULT, S_SEGACC, S_SEGRUN, S_PARTS, S_BA_X, S_BA_Y, S_BA_PREFIX, S_BA_CS, S_BA_CM, S_COUNT };
     MsmScratch s[S_COUNT];
     cudaEvent_t ev_sorted = nullptr, ev_accumulated = nullptr;
 };

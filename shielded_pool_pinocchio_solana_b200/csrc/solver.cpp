@@ -1,5 +1,6 @@
 // solver.cpp -- see solver.hpp.
 #include "solver.hpp"
+#include "hostbig.hpp"
 
 #include <string.h>
 
@@ -124,7 +125,11 @@ int run_hint(const Circuit& c, SolveState* st, uint32_t instr, const HFr* blinde
             std::vector<uint64_t> mult(size, 0);
             for (size_t q = 2 + size * cols; q < nin; q += cols) {
                 auto it = index.find(key_of(q));
-                if (it == index.end()) return fail(st, G16_E_HINT, "countHint: query not in table");
+                if (it == index.end()) {
+                    if (!st->tolerate) return fail(st, G16_E_HINT, "countHint: query not in table");
+                    for (uint32_t k = 0; k < nout; k++) set_out(k, HFr::zero());
+                    return G16_OK;
+                }
                 mult[it->second]++;
             }
             for (uint32_t k = 0; k < nout; k++) set_out(k, HFr::from_u64(mult[k]));
@@ -146,6 +151,123 @@ int run_hint(const Circuit& c, SolveState* st, uint32_t instr, const HFr* blinde
             *paused = true;
             return G16_OK;
         }
+        case HINT_EMULATED_MUL: {
+            // gnark std/math/emulated mulHint: quo | rem | carries with
+            //   a(X) b(X) = rem(X) + quo(X) p(X) + (2^nbBits - X) carry(X)   over the integers
+            // (restated in oracle/py/groth16.py `_hint_emulated_mul`)
+            if (nin < 6) return fail(st, G16_E_HINT, "emulated.mulHint: too few inputs");
+            uint64_t hdr[4];
+            for (int k = 0; k < 4; k++) {
+                uint64_t cn[4];
+                ins[k].canonical(cn);
+                if (cn[1] | cn[2] | cn[3] || cn[0] > 4096) return fail(st, G16_E_HINT, "emulated.mulHint: bad header");
+                hdr[k] = cn[0];
+            }
+            const size_t nbits = hdr[0], nlimbs = hdr[1], na = hdr[2], nquo = hdr[3];
+            if (nbits == 0 || nbits > 128 || nlimbs == 0 || 4 + nlimbs + na >= nin) return fail(st, G16_E_HINT, "emulated.mulHint: malformed inputs");
+            const size_t nb = nin - 4 - nlimbs - na;
+            const size_t ncarry = std::max(na + nb - 1, nquo + nlimbs - 1) - 1;
+            if (nout < nquo + ncarry) return fail(st, G16_E_HINT, "emulated.mulHint: output count mismatch");
+            const size_t nrem = nout - nquo - ncarry;
+            if (nrem != 0 && nrem != nlimbs) return fail(st, G16_E_HINT, "emulated.mulHint: output count mismatch");
+            std::vector<BigInt> pl(nlimbs), al(na), bl(nb);
+            for (size_t i = 0; i < nlimbs; i++) pl[i] = BigInt::from_fr(ins[4 + i]);
+            for (size_t i = 0; i < na; i++) al[i] = BigInt::from_fr(ins[4 + nlimbs + i]);
+            for (size_t i = 0; i < nb; i++) bl[i] = BigInt::from_fr(ins[4 + nlimbs + na + i]);
+            auto recompose = [&](const std::vector<BigInt>& l) {
+                BigInt v;
+                for (size_t i = l.size(); i-- > 0;) v = v.shl(nbits) + l[i];
+                return v;
+            };
+            const BigInt p = recompose(pl), a = recompose(al), b = recompose(bl);
+            if (p.is_zero()) return fail(st, G16_E_HINT, "emulated.mulHint: zero modulus");
+            BigInt quo, rem;
+            BigInt::divmod_mag(a * b, p, &quo, &rem);
+            if (nrem == 0 && !rem.is_zero()) return fail(st, G16_E_HINT, "emulated.mulHint: product is not a multiple of the modulus");
+            if (quo.bits() > nbits * nquo) return fail(st, G16_E_HINT, "emulated.mulHint: quotient does not fit");
+            std::vector<BigInt> ql(nquo), rl(nrem);
+            for (size_t i = 0; i < nquo; i++) ql[i] = quo.shr_mag(nbits * i).low_bits(nbits);
+            for (size_t i = 0; i < nrem; i++) rl[i] = rem.shr_mag(nbits * i).low_bits(nbits);
+            std::vector<BigInt> xp(na + nb - 1), yp(nquo + nlimbs - 1);
+            for (size_t i = 0; i < na; i++)
+                for (size_t j = 0; j < nb; j++) xp[i + j] = xp[i + j] + al[i] * bl[j];
+            for (size_t i = 0; i < nlimbs; i++) {
+                if (i < nrem) yp[i] = yp[i] + rl[i];
+                for (size_t j = 0; j < nquo; j++) yp[i + j] = yp[i + j] + ql[j] * pl[i];
+            }
+            for (size_t i = 0; i < nquo; i++) set_out((uint32_t)i, ql[i].to_fr());
+            for (size_t i = 0; i < nrem; i++) set_out((uint32_t)(nquo + i), rl[i].to_fr());
+            BigInt carry;
+            for (size_t i = 0; i < ncarry; i++) {
+                if (i < xp.size()) carry = carry + xp[i];
+                if (i < yp.size()) carry = carry - yp[i];
+                carry = carry.shr_floor(nbits);
+                set_out((uint32_t)(nquo + nrem + i), carry.to_fr());
+            }
+            return G16_OK;
+        }
+        case HINT_GRUMPKIN_LIMBS: {
+            // the native scalar as nout 64-bit limbs (its representation in the emulated scalar field)
+            if (nin != 1 || nout == 0 || nout > 4) return fail(st, G16_E_HINT, "sw-grumpkin.decompose: expected 1 input, <= 4 outputs");
+            uint64_t cn[4];
+            ins[0].canonical(cn);
+            for (uint32_t k = nout; k < 4; k++)
+                if (cn[k]) return fail(st, G16_E_HINT, "sw-grumpkin.decompose: scalar does not fit");
+            for (uint32_t k = 0; k < nout; k++) set_out(k, HFr::from_u64(cn[k]));
+            return G16_OK;
+        }
+        case HINT_GRUMPKIN_SPLIT: {
+            // s -> (s1, s2), 0 <= s1, s2 < 2^127, s1 = s + LAMBDA s2 (mod q): what instructions 18-21 and 150 of the
+            // withdraw circuit enforce.  The box can hold several such pairs and sunspot's own choice is not
+            // observable offline: smallest max(s1, s2), then smallest s2 (UNPINNED; oracle/py `glv_split_nonneg`).
+            static const BigInt Q = BigInt::from_decimal("21888242871839275222246405745257275088696311157297823662689037894645226208583");
+            static const BigInt A1 = BigInt::from_decimal("9931322734385697762");
+            static const BigInt B1 = BigInt::from_decimal("147946756881789319000765030803803410729");
+            static const BigInt A2 = BigInt::from_decimal("147946756881789319010696353538189108491");
+            static const BigInt B2 = -BigInt::from_decimal("9931322734385697762");
+            uint64_t cn[4];
+            if (nin < 9) return fail(st, G16_E_HINT, "sw-grumpkin.decomposeScalar: unexpected input framing");
+            auto small = [&](size_t k, uint64_t* v) {
+                ins[k].canonical(cn);
+                *v = cn[0];
+                return !(cn[1] | cn[2] | cn[3]);
+            };
+            uint64_t n_native, n_out, nlimbs, nbits;
+            if (!small(0, &n_native) || !small(3, &n_out) || !small(7, &nlimbs) || !small(8, &nbits) || n_native != 1 || n_out != 2 ||
+                nlimbs != 4 || nbits != 64 || nin != 9 + nlimbs || nout != n_out * nlimbs)
+                return fail(st, G16_E_HINT, "sw-grumpkin.decomposeScalar: unexpected input framing");
+            BigInt mod;
+            for (size_t i = nlimbs; i-- > 0;) mod = mod.shl(nbits) + BigInt::from_fr(ins[9 + i]);
+            if (!(mod == Q)) return fail(st, G16_E_HINT, "sw-grumpkin.decomposeScalar: not the Grumpkin scalar field");
+            BigInt s, sq, sr;
+            BigInt::divmod_mag(BigInt::from_fr(ins[6]), Q, &sq, &s);
+            const BigInt det = A1 * B2 - B1 * A2;   // = -q
+            const BigInt half = BigInt(1).shl(126), top = BigInt(1).shl(127);
+            const BigInt tx = s - half, ty = -half;
+            // floor((tx*B2 - ty*A2) / det) with det < 0: negate numerator and denominator
+            const BigInt c1 = BigInt::floordiv(-(tx * B2 - ty * A2), -det);
+            const BigInt c2 = BigInt::floordiv(-(ty * A1 - tx * B1), -det);
+            bool have = false;
+            BigInt bx, by, bkey;
+            for (int d1 = -2; d1 < 4; d1++)
+                for (int d2 = -2; d2 < 4; d2++) {
+                    const BigInt k1 = c1 + (d1 < 0 ? -BigInt((uint64_t)-d1) : BigInt((uint64_t)d1));
+                    const BigInt k2 = c2 + (d2 < 0 ? -BigInt((uint64_t)-d2) : BigInt((uint64_t)d2));
+                    const BigInt x = s - k1 * A1 - k2 * A2, y = -(k1 * B1) - k2 * B2;
+                    if (x.neg || y.neg || !(x < top) || !(y < top)) continue;
+                    const BigInt key = x < y ? y : x;
+                    if (!have || key < bkey || (key == bkey && y < by)) {
+                        have = true;
+                        bx = x; by = y; bkey = key;
+                    }
+                }
+            if (!have) return fail(st, G16_E_HINT, "sw-grumpkin.decomposeScalar: no decomposition in range");
+            for (uint32_t k = 0; k < 4; k++) {
+                set_out(k, bx.shr_mag(64 * k).low_bits(64).to_fr());
+                set_out(4 + k, by.shr_mag(64 * k).low_bits(64).to_fr());
+            }
+            return G16_OK;
+        }
         default: {
             auto nm = c.hint_names.find(hid);
             return fail(st, G16_E_HINT, "solver hint not implemented: " + (nm == c.hint_names.end() ? std::to_string(hid) : nm->second));
@@ -164,7 +286,10 @@ int run_r1c(const Circuit& c, SolveState* st, uint32_t instr) {
     int unknowns = L.unknowns + Rr.unknowns + O.unknowns;
     const uint32_t row = c.constraint_offset[instr];
     if (unknowns == 0) {
-        if (L.sum * Rr.sum != O.sum) return fail(st, G16_E_UNSAT, "constraint #" + std::to_string(row) + " is not satisfied");
+        if (L.sum * Rr.sum != O.sum) {
+            if (!st->tolerate) return fail(st, G16_E_UNSAT, "constraint #" + std::to_string(row) + " is not satisfied");
+            st->failed_rows++;
+        }
         return G16_OK;
     }
     // gnark's blueprint guarantees one unknown wire per row, appearing on one side
@@ -182,14 +307,20 @@ int run_r1c(const Circuit& c, SolveState* st, uint32_t instr) {
         // gnark solveR1C: with a zero divisor the wire stays 0 and the row is only checked (a*b == c),
         // the DivUnchecked(0, 0) = 0 convention
         if (Rr.sum.is_zero()) {
-            if (!O.sum.is_zero()) return fail(st, G16_E_UNSAT, "constraint #" + std::to_string(row) + " is not satisfied");
+            if (!O.sum.is_zero()) {
+                if (!st->tolerate) return fail(st, G16_E_UNSAT, "constraint #" + std::to_string(row) + " is not satisfied");
+                st->failed_rows++;
+            }
             val = HFr::zero();
         } else {
             val = (O.sum * Rr.sum.inverse() - L.sum) * coeff_inv(L);
         }
     } else {
         if (L.sum.is_zero()) {
-            if (!O.sum.is_zero()) return fail(st, G16_E_UNSAT, "constraint #" + std::to_string(row) + " is not satisfied");
+            if (!O.sum.is_zero()) {
+                if (!st->tolerate) return fail(st, G16_E_UNSAT, "constraint #" + std::to_string(row) + " is not satisfied");
+                st->failed_rows++;
+            }
             val = HFr::zero();
         } else {
             val = (O.sum * L.sum.inverse() - Rr.sum) * coeff_inv(Rr);
