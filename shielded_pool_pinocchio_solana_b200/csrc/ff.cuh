@@ -398,6 +398,15 @@ struct alignas(16) Field {
 typedef Field<FpParams> Fp;
 typedef Field<FrParams> Fr;
 
+// Fp product as a real call on the device: an Fp2 point addition is 28 base-field products; inlined, the G2 bucket
+// kernels are ~100 KB of straight-line SASS and stall on instruction fetch.
+#ifdef __CUDA_ARCH__
+static __device__ __noinline__ Fp fp_mul_call(Fp a, Fp b) { return a * b; }
+#define FP2_MUL(a, b) fp_mul_call((a), (b))
+#else
+#define FP2_MUL(a, b) ((a) * (b))
+#endif
+
 // ---- Fp2 = Fp[u]/(u^2+1) ------------------------------------------------------------------
 struct Fp2 {
     Fp c0, c1;
@@ -412,15 +421,15 @@ struct Fp2 {
     FF_HD Fp2 dbl() const { return {c0.dbl(), c1.dbl()}; }
     // Karatsuba: 3 base multiplications
     FF_HD friend Fp2 operator*(const Fp2& a, const Fp2& b) {
-        Fp t0 = a.c0 * b.c0;
-        Fp t1 = a.c1 * b.c1;
-        Fp t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
+        Fp t0 = FP2_MUL(a.c0, b.c0);
+        Fp t1 = FP2_MUL(a.c1, b.c1);
+        Fp t2 = FP2_MUL(a.c0 + a.c1, b.c0 + b.c1);
         return {t0 - t1, t2 - t0 - t1};
     }
     // (a0+a1)(a0-a1) + 2 a0 a1 u : 2 base multiplications
     FF_HD Fp2 sqr() const {
-        Fp t0 = (c0 + c1) * (c0 - c1);
-        Fp t1 = c0 * c1;
+        Fp t0 = FP2_MUL(c0 + c1, c0 - c1);
+        Fp t1 = FP2_MUL(c0, c1);
         return {t0, t1.dbl()};
     }
     FF_HD Fp2 inverse() const {
