@@ -86,6 +86,25 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE line (the JSON record): anything a library prints there at the C level (NCCL's
+    version banner at communicator creation, for one) is sent to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -238,7 +257,7 @@ def run_reference(args):
                              "latency_mode": latency_rate, "sustained_mode": sustained_rate},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -328,6 +347,7 @@ def main():
                     help="2^22 single proof split across the ranks (configs[3]); auto = only when N > 1")
     ap.add_argument("--single-log", type=int, default=22)
     args = ap.parse_args()
+    quiet_stdout()
     rank, world, local = dist_env()
     if world != args.gpus and world != 1:
         args.gpus = world
@@ -530,7 +550,7 @@ def main():
                                                   "the sustained one-prover-per-core mode" % (done, dt)}
             except Exception as e:                       # noqa: BLE001 -- a reported baseline must not sink the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if use_dist:
         dist.destroy_process_group()
