@@ -368,6 +368,7 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
+    ctx.set_deferred_join(True)          # consecutive g16_prove_wires_dev calls overlap; timed() joins before its end event
 
     # ---- workload: circuits, keys (GPU setup, untimed), wires ---------------------------------------------
     real_ccs = open(REAL_CCS, "rb").read()
@@ -435,6 +436,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         launches = fn()
+        ctx.join()                       # deferred joins: the context stream now waits for every chunk's assembly
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)

@@ -56,6 +56,13 @@ const char* g16_last_error(void);
  * torch.cuda.current_stream().cuda_stream); NULL restores the context's own stream. */
 int g16_set_stream(g16_ctx* ctx, void* cuda_stream);
 int g16_sync(g16_ctx* ctx);
+/* Device-side calls (g16_prove_wires_dev) normally end by making the context stream wait for their last kernel, so
+ * that their outputs are ordered on that stream.  With deferred joins ON they return without that wait: consecutive
+ * calls then overlap on the device (the latency-bound end of one under the start of the next).  Outputs are
+ * complete once work enqueued after g16_join(ctx) -- which inserts the pending waits into the context stream --
+ * runs, or after g16_sync.  Host-side calls (g16_prove*, g16_prove_batch, g16_prove_wires) are unaffected. */
+int g16_set_deferred_join(g16_ctx* ctx, int on);
+int g16_join(g16_ctx* ctx);
 /* kernels launched by the last compute call on this context (bench.py `gpu_launches`) */
 int g16_last_launches(g16_ctx* ctx);
 /* Per-kernel device timing with CUDA events on the context stream (bench.py's roofline line).

@@ -35,6 +35,13 @@ class Context:
         assert len(unique_id) == 128
         check(self.lib.g16_comm_init(self.handle, unique_id, rank, world))
 
+    def set_deferred_join(self, on=True):
+        """prove_wires_dev calls stop joining the context stream (they overlap); call join() before using outputs."""
+        check(self.lib.g16_set_deferred_join(self.handle, int(bool(on))))
+
+    def join(self):
+        check(self.lib.g16_join(self.handle))
+
     def set_stream(self, cuda_stream):
         check(self.lib.g16_set_stream(self.handle, ctypes.c_void_p(cuda_stream)))
 

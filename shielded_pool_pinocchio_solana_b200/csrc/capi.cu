@@ -205,6 +205,7 @@ int g16_sync(g16_ctx* ctx) {
     if (!ctx) return G16_E_ARG;
     G16_CUDA(cudaSetDevice(ctx->device));
     G16_LOCK(ctx);
+    G16_TRY(g16_join(ctx));
     G16_CUDA(cudaStreamSynchronize(ctx->stream));
     return G16_OK;
 }

@@ -33,6 +33,7 @@ void shard_range(size_t n, int rank, int world, size_t* lo, size_t* hi);
 // context per thread.
 #define G16_LOCK(ctxptr) std::lock_guard<std::recursive_mutex> _g16_lock((ctxptr)->mu)
 
+struct g16_circuit;
 struct g16_ctx {
     std::recursive_mutex mu;
     int device = 0;
@@ -49,6 +50,10 @@ struct g16_ctx {
     void* comm = nullptr;
     int rank = 0, world = 1;
     g16::DeviceBuf comm_recv;
+    // g16_set_deferred_join: device-side calls (g16_prove_wires_dev) return without making the context stream wait
+    // for their assembly; g16_join / g16_sync / the next use of the same buffers do.  Lets consecutive calls overlap.
+    bool deferred_join = false;
+    std::vector<g16_circuit*> circuits;   // loaded on this context (g16_join walks them)
 };
 
 namespace g16 {

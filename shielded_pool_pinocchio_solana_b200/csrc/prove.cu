@@ -15,6 +15,7 @@
 
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <fstream>
 #include <future>
@@ -277,7 +278,14 @@ g16_circuit::~g16_circuit() {
     }
     cudaFree(d_coeffs);
     cudaFree(d_mapA); cudaFree(d_mapB); cudaFree(d_mapKZ); cudaFree(d_mapPok);
-    cudaFree(d_tmp_g1); cudaFree(d_tmp_g2); cudaFree(d_parts);
+    if (ctx) cudaDeviceSynchronize();   // deferred chunks may still be in flight on the private streams
+    for (int p = 0; p < 2; p++) {
+        cudaFree(d_tmp_g1[p]); cudaFree(d_tmp_g2[p]); cudaFree(d_parts[p]);
+        if (ev_fin[p]) cudaEventDestroy(ev_fin[p]);
+    }
+    if (fin_stream) cudaStreamDestroy(fin_stream);
+    g1_kz.release();
+    if (ctx) ctx->circuits.erase(std::remove(ctx->circuits.begin(), ctx->circuits.end(), this), ctx->circuits.end());
     cudaFree(d_map_commit);
     for (auto& sl : slots) {
         if (sl.h_stage) cudaFreeHost(sl.h_stage);
@@ -363,11 +371,31 @@ void parallel_for(size_t n, Fn fn) {
     for (auto& x : th) x.join();
 }
 
-// Device part of the pipeline: W = B wire vectors (stride wstride, X_* slots filled) in HBM.
-int prove_device(g16_circuit* c, size_t B, const Fr* W) {
+// Buffer set for the next chunk: the context stream waits until the chunk that last used it has been assembled.
+// Call BEFORE staging that chunk's wires into d_wdev[p] / a pipeline slot.
+int chunk_begin(g16_circuit* c, int* parity) {
+    const int p = c->parity;
+    c->parity ^= 1;
+    G16_CUDA(cudaStreamWaitEvent(c->ctx->stream, c->ev_fin[p], 0));
+    *parity = p;
+    return G16_OK;
+}
+
+// The caller has enqueued whatever consumes d_out[p] on chunk_stream(c): mark the set reusable behind it and, unless
+// joins are deferred, make the context stream wait (results are then ordered on the context stream as usual).
+cudaStream_t chunk_stream(g16_circuit* c) { return c->ctx->prof.enabled ? c->ctx->stream : c->fin_stream; }
+int chunk_end(g16_circuit* c, int p, bool defer) {
+    G16_CUDA(cudaEventRecord(c->ev_fin[p], chunk_stream(c)));
+    if (!defer) G16_CUDA(cudaStreamWaitEvent(c->ctx->stream, c->ev_fin[p], 0));
+    return G16_OK;
+}
+
+// Device part of the pipeline: W = B wire vectors (stride wstride, X_* slots filled) in HBM; buffer set p
+// (chunk_begin).  The assembled proof points land in d_out[p] on chunk_stream(c).
+int prove_device(g16_circuit* c, size_t B, const Fr* W, int p) {
     g16_ctx* ctx = c->ctx;
     cudaStream_t st = ctx->stream;
-    Fr* abc = (Fr*)c->d_abc.ptr;
+    Fr* abc = (Fr*)c->d_abc[p].ptr;
     int launches = 0;
     if (!ctx->prof.enabled) {   // side streams start once the wires are in place
         G16_CUDA(cudaEventRecord(c->ev_fork, st));
@@ -384,10 +412,13 @@ int prove_device(g16_circuit* c, size_t B, const Fr* W) {
     G16_TRY(ctx->ntt.compute_h(abc, c->logn, B, st));
     ctx->prof.mark("quotient", "done", st);
     launches += ctx->ntt.launches;
-    G1Affine* rA = c->d_tmp_g1;
-    G1Affine* rB1 = c->d_tmp_g1 + c->max_batch;
-    G1Affine* rKZ = c->d_tmp_g1 + 2 * c->max_batch;
-    G1Affine* rPok = c->d_tmp_g1 + 3 * c->max_batch;
+    G1Affine* rA = c->d_tmp_g1[p];
+    G1Affine* rB1 = c->d_tmp_g1[p] + c->max_batch;
+    G1Affine* rKZ = c->d_tmp_g1[p] + 2 * c->max_batch;
+    G1Affine* rPok = c->d_tmp_g1[p] + 3 * c->max_batch;
+    G2Affine* rB2 = c->d_tmp_g2[p];
+    G1XYZZ* parts = c->d_parts[p];
+    cudaStream_t sFin = chunk_stream(c);
     // per-kernel profiling wants serial, un-overlapped launches
     const bool overlap = !ctx->prof.enabled;
     auto on = [&](int i) { return overlap ? c->side[i] : st; };
@@ -406,8 +437,9 @@ int prove_device(g16_circuit* c, size_t B, const Fr* W) {
     c->g1_side[1].label = "B1";
     c->g1_side[2].label = "PoK";
     c->g2_side.label = "B2";
-    ctx->g1.label = "KZ";
-    G16_TRY(c->g2_side.run(c->bB2, W, c->wstride, c->d_mapB, 1, B, c->d_tmp_g2, sB2));   // the longest side chain first
+    c->g1_kz.prof = &ctx->prof;
+    c->g1_kz.label = "KZ";
+    G16_TRY(c->g2_side.run(c->bB2, W, c->wstride, c->d_mapB, 1, B, rB2, sB2));   // the longest side chain first
     launches += c->g2_side.launches;
     G16_TRY(c->g1_side[0].run(c->bA, W, c->wstride, c->d_mapA, 1, B, rA, sA));
     launches += c->g1_side[0].launches;
@@ -421,7 +453,7 @@ int prove_device(g16_circuit* c, size_t B, const Fr* W) {
             G16_CUDA(cudaStreamWaitEvent(sSm, c->ev_join[g16_circuit::SIDE_A], 0));
             G16_CUDA(cudaStreamWaitEvent(sSm, c->ev_join[g16_circuit::SIDE_B1], 0));
         }
-        k_scalar_muls<<<(unsigned)B, 64, 0, sSm>>>(rA, rB1, W, c->wstride, c->nw, (uint32_t)c->max_batch, c->d_parts);
+        k_scalar_muls<<<(unsigned)B, 64, 0, sSm>>>(rA, rB1, W, c->wstride, c->nw, (uint32_t)c->max_batch, parts);
         ctx->prof.mark("scalar_muls", "done", sSm);
         launches++;
     }
@@ -436,10 +468,9 @@ int prove_device(g16_circuit* c, size_t B, const Fr* W) {
         G16_CUDA(cudaEventRecord(c->ev_h, st));
         G16_CUDA(cudaStreamWaitEvent(sKZ, c->ev_h, 0));
     }
-    ctx->g1.acc_stream = low_acc ? c->acc_stream : nullptr;
-    G16_TRY(ctx->g1.run(c->bKZ, W, c->wstride, c->d_mapKZ, 1, B, rKZ, sKZ, abc, 3 * c->n));
-    ctx->g1.acc_stream = nullptr;
-    launches += ctx->g1.launches;
+    c->g1_kz.acc_stream = low_acc ? c->acc_stream : nullptr;
+    G16_TRY(c->g1_kz.run(c->bKZ, W, c->wstride, c->d_mapKZ, 1, B, rKZ, sKZ, abc, 3 * c->n));
+    launches += c->g1_kz.launches;
     if (overlap) {
         // A and B1 are joined through SIDE_SM (which waited for both) unless the circuit is split across ranks
         const int first = split ? g16_circuit::SIDE_A : g16_circuit::SIDE_POK;
@@ -452,17 +483,16 @@ int prove_device(g16_circuit* c, size_t B, const Fr* W) {
         if (!split) G16_CUDA(cudaEventRecord(c->ev_join[g16_circuit::SIDE_SM], sSm));
         G16_CUDA(cudaEventRecord(c->ev_join[g16_circuit::SIDE_KZ], sKZ));
         for (int i = first; i < g16_circuit::N_SIDE; i++)
-            if (!(split && i == g16_circuit::SIDE_SM)) G16_CUDA(cudaStreamWaitEvent(st, c->ev_join[i], 0));
+            if (!(split && i == g16_circuit::SIDE_SM)) G16_CUDA(cudaStreamWaitEvent(sFin, c->ev_join[i], 0));
     }
     if (ctx->world > 1) {   // partial sums of this rank's point ranges -> sums over all ranks (tiny NCCL all-gather)
-        G16_TRY(comm_sum_points<Fp>(ctx, c->d_tmp_g1, 4 * c->max_batch, st));
-        G16_TRY(comm_sum_points<Fp2>(ctx, c->d_tmp_g2, c->max_batch, st));
-        k_scalar_muls<<<(unsigned)B, 64, 0, st>>>(rA, rB1, W, c->wstride, c->nw, (uint32_t)c->max_batch, c->d_parts);
+        G16_TRY(comm_sum_points<Fp>(ctx, c->d_tmp_g1[p], 4 * c->max_batch, sFin));
+        G16_TRY(comm_sum_points<Fp2>(ctx, rB2, c->max_batch, sFin));
+        k_scalar_muls<<<(unsigned)B, 64, 0, sFin>>>(rA, rB1, W, c->wstride, c->nw, (uint32_t)c->max_batch, parts);
         launches += 3;
     }
-    k_finalize<<<(unsigned)B, 32, 0, st>>>(rA, c->d_parts, (uint32_t)c->max_batch, c->d_tmp_g2, rKZ, rPok,
-                                           (ProofPoints*)c->d_out.ptr);
-    ctx->prof.mark("finalize", "done", st);
+    k_finalize<<<(unsigned)B, 32, 0, sFin>>>(rA, parts, (uint32_t)c->max_batch, rB2, rKZ, rPok, (ProofPoints*)c->d_out[p].ptr);
+    ctx->prof.mark("finalize", "done", sFin);
     launches++;
     G16_CUDA(cudaGetLastError());
     c->last_launches = launches;
@@ -638,8 +668,12 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
     G16_CUDA(cudaMalloc(&c->d_coeffs, sizeof(Fr) * circ.coeffs.size()));
     G16_CUDA(cudaMemcpyAsync(c->d_coeffs, circ.coeffs.data(), sizeof(Fr) * circ.coeffs.size(), cudaMemcpyHostToDevice, st));
     // ---- scratch -------------------------------------------------------------------------------
-    G16_TRY(c->d_abc.ensure(sizeof(Fr) * 3 * c->n * max_batch));
-    G16_TRY(c->d_out.ensure(sizeof(ProofPoints) * max_batch));
+    for (int p = 0; p < 2; p++) {
+        G16_TRY(c->d_abc[p].ensure(sizeof(Fr) * 3 * c->n * max_batch));
+        G16_TRY(c->d_out[p].ensure(sizeof(ProofPoints) * max_batch));
+        G16_TRY(c->d_wdev[p].ensure(sizeof(Fr) * c->wstride * max_batch));
+        G16_CUDA(cudaEventCreateWithFlags(&c->ev_fin[p], cudaEventDisableTiming));
+    }
     {
         int lo = 0, hi = 0;
         G16_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -658,6 +692,11 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
     }
     G16_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     G16_CUDA(cudaEventCreateWithFlags(&c->ev_h, cudaEventDisableTiming));
+    {
+        int lo = 0, hi = 0;
+        G16_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        G16_CUDA(cudaStreamCreateWithPriority(&c->fin_stream, cudaStreamNonBlocking, hi < lo ? hi + 1 : hi));
+    }
     for (int i = 0; i < 2; i++) {
         G16_CUDA(cudaMallocHost((void**)&c->h_pts[i], sizeof(ProofPoints) * max_batch));
         G16_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
@@ -681,15 +720,34 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
     } else {
         c->host_solver_reason = "G16_HOST_SOLVER is set";
     }
-    G16_CUDA(cudaMalloc(&c->d_tmp_g1, sizeof(G1Affine) * 4 * max_batch));
-    G16_CUDA(cudaMalloc(&c->d_tmp_g2, sizeof(G2Affine) * max_batch));
-    G16_CUDA(cudaMalloc(&c->d_parts, sizeof(G1XYZZ) * 2 * max_batch));
-    G16_CUDA(cudaMemsetAsync(c->d_tmp_g1, 0, sizeof(G1Affine) * 4 * max_batch, st));   // unused slots = infinity
-    G16_CUDA(cudaMemsetAsync(c->d_tmp_g2, 0, sizeof(G2Affine) * max_batch, st));
+    for (int p = 0; p < 2; p++) {
+        G16_CUDA(cudaMalloc(&c->d_tmp_g1[p], sizeof(G1Affine) * 4 * max_batch));
+        G16_CUDA(cudaMalloc(&c->d_tmp_g2[p], sizeof(G2Affine) * max_batch));
+        G16_CUDA(cudaMalloc(&c->d_parts[p], sizeof(G1XYZZ) * 2 * max_batch));
+        G16_CUDA(cudaMemsetAsync(c->d_tmp_g1[p], 0, sizeof(G1Affine) * 4 * max_batch, st));   // unused slots = infinity
+        G16_CUDA(cudaMemsetAsync(c->d_tmp_g2[p], 0, sizeof(G2Affine) * max_batch, st));
+    }
     const NttDomain* dom;
     G16_TRY(ctx->ntt.domain(c->logn, st, &dom));
     G16_CUDA(cudaStreamSynchronize(st));
+    ctx->circuits.push_back(c.get());
     *out = c.release();
+    return G16_OK;
+}
+
+int g16_set_deferred_join(g16_ctx* ctx, int on) {
+    if (!ctx) return G16_E_ARG;
+    G16_LOCK(ctx);
+    ctx->deferred_join = on != 0;
+    return G16_OK;
+}
+
+int g16_join(g16_ctx* ctx) {
+    if (!ctx) return G16_E_ARG;
+    G16_CUDA(cudaSetDevice(ctx->device));
+    G16_LOCK(ctx);
+    for (g16_circuit* c : ctx->circuits)
+        for (int p = 0; p < 2; p++) G16_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_fin[p], 0));
     return G16_OK;
 }
 
@@ -746,15 +804,17 @@ int g16_prove_wires_dev(g16_circuit* c, size_t n, const void* d_wires, const uin
         fill_extra_slots(extras.data() + X_COUNT * b, r, s);
     }
     // wires arrive without the X_* slots: lay them out with stride wstride, then drop the extras in
-    Fr* W = (Fr*)c->slots[0].d_wires.ptr;
+    int p;
+    G16_TRY(chunk_begin(c, &p));
+    Fr* W = (Fr*)c->d_wdev[p].ptr;
     G16_CUDA(cudaMemcpy2DAsync(W, sizeof(Fr) * c->wstride, d_wires, sizeof(Fr) * c->nw, sizeof(Fr) * c->nw, n,
                                cudaMemcpyDeviceToDevice, st));
     // pageable source: the runtime stages it before returning, so `extras` may go out of scope
     G16_CUDA(cudaMemcpy2DAsync(W + c->nw, sizeof(Fr) * c->wstride, extras.data(), sizeof(Fr) * X_COUNT,
                                sizeof(Fr) * X_COUNT, n, cudaMemcpyHostToDevice, st));
-    G16_TRY(prove_device(c, n, W));
-    G16_CUDA(cudaMemcpyAsync(d_proof_points, c->d_out.ptr, sizeof(ProofPoints) * n, cudaMemcpyDeviceToDevice, st));
-    return G16_OK;
+    G16_TRY(prove_device(c, n, W, p));
+    G16_CUDA(cudaMemcpyAsync(d_proof_points, c->d_out[p].ptr, sizeof(ProofPoints) * n, cudaMemcpyDeviceToDevice, chunk_stream(c)));
+    return chunk_end(c, p, c->ctx->deferred_join);
 }
 
 // Shared host path: `wires` holds n full wire vectors (Montgomery) with stride wstride and the X_*
@@ -765,10 +825,14 @@ static int prove_from_host_wires(g16_circuit* c, size_t n, const HFr* wires, con
     size_t bytes = sizeof(Fr) * c->wstride * n;
     g16_circuit::Slot& sl = c->slots[0];
     if ((const void*)wires != sl.h_wires) memcpy(sl.h_wires, wires, bytes);
+    int p;
+    G16_TRY(chunk_begin(c, &p));
+    G16_CUDA(cudaStreamSynchronize(c->fin_stream));   // synchronous path: the slot is reused right away
     G16_CUDA(cudaMemcpyAsync(sl.d_wires.ptr, sl.h_wires, bytes, cudaMemcpyHostToDevice, st));
-    G16_TRY(prove_device(c, n, (const Fr*)sl.d_wires.ptr));
+    G16_TRY(prove_device(c, n, (const Fr*)sl.d_wires.ptr, p));
     std::vector<ProofPoints> pts(n);
-    G16_CUDA(cudaMemcpyAsync(pts.data(), c->d_out.ptr, sizeof(ProofPoints) * n, cudaMemcpyDeviceToHost, st));
+    G16_CUDA(cudaMemcpyAsync(pts.data(), c->d_out[p].ptr, sizeof(ProofPoints) * n, cudaMemcpyDeviceToHost, chunk_stream(c)));
+    G16_TRY(chunk_end(c, p, false));
     G16_CUDA(cudaStreamSynchronize(st));
     const size_t plen = c->has_commitment ? 388 : 324;
     for (size_t b = 0; b < n; b++)
@@ -1110,10 +1174,13 @@ static int run_pipeline(g16_circuit* c, size_t n, Launch launch, uint8_t* proofs
             const size_t B = std::min(c->max_batch, G - off), first = g * SB + off;
             const int ring = (int)(chunk_no++ & 1);
             trace("pipeline: chunk begin", (long)first);
-            if ((rc = prove_device(c, B, (const Fr*)sl.d_wires.ptr + off * c->wstride)) != G16_OK) break;
+            int p = 0;
+            if ((rc = chunk_begin(c, &p)) != G16_OK) break;
+            if ((rc = prove_device(c, B, (const Fr*)sl.d_wires.ptr + off * c->wstride, p)) != G16_OK) break;
             total_launches += c->last_launches;
-            if (cudaMemcpyAsync(c->h_pts[ring], c->d_out.ptr, sizeof(ProofPoints) * B, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-                cudaEventRecord(c->ev_done[ring], st) != cudaSuccess) {
+            // consecutive chunks are independent on the device (two buffer sets): no join on the context stream
+            if (cudaMemcpyAsync(c->h_pts[ring], c->d_out[p].ptr, sizeof(ProofPoints) * B, cudaMemcpyDeviceToHost, chunk_stream(c)) != cudaSuccess ||
+                cudaEventRecord(c->ev_done[ring], chunk_stream(c)) != cudaSuccess || chunk_end(c, p, true) != G16_OK) {
                 rc = G16_E_CUDA;
                 set_error(std::string("device pipeline: ") + cudaGetErrorString(cudaGetLastError()));
                 break;

@@ -65,11 +65,18 @@ struct g16_circuit {
     g16::MsmBases<g16::Fp2> bB2;
     uint32_t *d_mapA = nullptr, *d_mapB = nullptr, *d_mapKZ = nullptr, *d_mapPok = nullptr;
     size_t nA = 0, nB = 0, nK = 0, nZ = 0;
-    // scratch sized for max_batch proofs
-    g16::DeviceBuf d_abc, d_out;
-    g16::G1Affine* d_tmp_g1 = nullptr;   // [4][max_batch]: A, B1, KZ, PoK results (Montgomery)
-    g16::G2Affine* d_tmp_g2 = nullptr;   // [max_batch]
-    g16::G1XYZZ* d_parts = nullptr;      // [2][max_batch]: s*Ar, r*Bs1
+    // Scratch sized for max_batch proofs, TWO sets used alternately (`parity`): consecutive chunks are independent on
+    // the device, so the latency-bound end of chunk k (K|Z bucket reduction, assembly: ~2 ms on a few hundred
+    // threads) runs under the start of chunk k+1.  ev_fin[p] = the chunk that used set p has been assembled
+    // (and its outputs copied wherever the caller wanted them); set p is reused only behind it.
+    int parity = 0;
+    g16::DeviceBuf d_abc[2], d_out[2], d_wdev[2];
+    g16::G1Affine* d_tmp_g1[2] = {nullptr, nullptr};   // [4][max_batch]: A, B1, KZ, PoK results (Montgomery)
+    g16::G2Affine* d_tmp_g2[2] = {nullptr, nullptr};   // [max_batch]
+    g16::G1XYZZ* d_parts[2] = {nullptr, nullptr};      // [2][max_batch]: s*Ar, r*Bs1
+    cudaStream_t fin_stream = nullptr;                 // joins the MSM streams; assembly and output copies
+    cudaEvent_t ev_fin[2] = {nullptr, nullptr};
+    g16::MsmRunner<g16::Fp> g1_kz;                     // K|Z MSM (own scratch: chunks of different circuits overlap)
     // Two pipeline slots: while the device proves chunk k out of slot k%2, the host solves chunk
     // k+1 into the other slot (its commitment MSM runs on `aux_stream` with its own MSM scratch).
     struct Slot {

@@ -14,6 +14,7 @@ ctx = g16.Context(0)
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 ctx.set_stream(stream.cuda_stream)
+ctx.set_deferred_join(os.environ.get("G16_DEFER", "1") != "0")
 if os.environ.get("G16_SERIAL"):
     ctx.profile_enable(True)        # single stream, no overlap: clean per-phase durations in the timeline
 real_ccs = open(bench.REAL_CCS, "rb").read()
@@ -50,6 +51,7 @@ for name, ccs in (("withdraw", real_ccs), ("audit_like", sc_a.ccs)):
         e0.record(stream)
         for i in range(reps):
             circ.prove_wires_dev(sets[i % 2].data_ptr(), B, obuf.data_ptr(), rnd)
+        ctx.join()
         e1.record(stream)
         torch.cuda.synchronize()
         out[(name, dist)] = e0.elapsed_time(e1) / reps
