@@ -188,7 +188,10 @@ __device__ __forceinline__ Fr shfl_xor_fr(uint32_t mask, const Fr& a, int d) {
 
 // rec[2k]   = (mode, defined wire, coefficient id of the defined wire's term, constraint row)
 // rec[2k+1] = (calldata offset of the instruction, nL, nR, nO)          k = position in level order
-__global__ void __launch_bounds__(SOLVE_THREADS)
+#ifndef SOLVE_MIN_CTAS
+#define SOLVE_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MIN_CTAS)
 k_solve_tpi(const uint32_t* __restrict__ lvl_off, const uint4* __restrict__ rec, const uint32_t* __restrict__ calldata,
             const Fr* __restrict__ coeffs, const Fr* __restrict__ coeff_invs, Fr* wires, size_t wstride,
             size_t blinder_slot, uint32_t lvl_begin, uint32_t lvl_end, int unit_ids, uint32_t* err) {

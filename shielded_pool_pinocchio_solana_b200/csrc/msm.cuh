@@ -74,24 +74,49 @@ k_msm_digits(const Fr* __restrict__ scalars, size_t scalar_stride, const Fr* __r
              int montgomery, MsmConfig cfg, uint32_t* __restrict__ counts_or_cursor,
              uint32_t* __restrict__ entries) {
     __shared__ uint32_t sk[8][MSM_DIGIT_THREADS];
+    __shared__ uint32_t big_list[MSM_DIGIT_THREADS];
+    __shared__ uint32_t big_count;
     const uint32_t i = blockIdx.x * MSM_DIGIT_THREADS + threadIdx.x;
     const uint32_t b = blockIdx.y;
     const bool live = i < n;
+    if (threadIdx.x == 0) big_count = 0;
     Fr k = Fr::zero();
     if (live) {
         // map entries with bit 31 set read the second scalar source (e.g. the quotient H next to the wires)
         uint32_t si = map ? map[i] : i;
         k = (si >> 31) ? scalars1[(size_t)b * scalar_stride1 + (si & 0x7fffffffu)]
                        : scalars[(size_t)b * scalar_stride + si];
-        if (montgomery) k = k.from_mont();
+        // most wires of a real witness are 0 or 1: skip the Montgomery reduction for those
+        if (montgomery && !k.is_zero()) k = (k == Fr::one()) ? Fr{{1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}} : k.from_mont();
     }
 #pragma unroll
     for (int l = 0; l < 8; l++) sk[l][threadIdx.x] = k.v[l];
     uint32_t* base = counts_or_cursor + (size_t)b * cfg.nb;
-    const uint32_t* s = &sk[0][threadIdx.x];
     const int c = cfg.c;
     const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    // one warp-aggregated histogram / scatter step: lanes with the same bucket share one atomic
+    auto emit = [&](bool valid, uint32_t key, uint32_t entry) {
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? key : 0xffffffffu);
+        const uint32_t leader = __ffs(peers) - 1, rank = __popc(peers & lt);
+        uint32_t pos = 0;
+        if (valid && lane == leader) pos = atomicAdd(base + key, (uint32_t)__popc(peers));
+        pos = __shfl_sync(0xffffffffu, pos, leader);
+        if (PASS == 1 && valid) entries[pos + rank] = entry;
+    };
+    // ---- scalars below 2^(c-1) (zero, one, bytes: ~90 % of a witness) have a single digit, in window 0 ----------
+    const bool small = (k.v[1] | k.v[2] | k.v[3] | k.v[4] | k.v[5] | k.v[6] | k.v[7]) == 0 && k.v[0] <= half;
+    emit(live && small && k.v[0] != 0, k.v[0] - 1, i);
+    // ---- the others are compacted and walked window by window by full warps ---------------------------------------
+    __syncthreads();
+    if (live && !small) big_list[atomicAdd(&big_count, 1u)] = threadIdx.x;
+    __syncthreads();
+    const uint32_t nbig = big_count;
+    if ((threadIdx.x & ~31u) >= nbig) return;   // whole warp idle
+    const bool mine = threadIdx.x < nbig;
+    const uint32_t src = mine ? big_list[threadIdx.x] : 0;
+    const uint32_t gi = blockIdx.x * MSM_DIGIT_THREADS + src;
+    const uint32_t* s = &sk[0][src];
     uint32_t carry = 0;
     for (int j = 0; j < cfg.W; j++) {
         int bit = j * c;
@@ -106,14 +131,7 @@ k_msm_digits(const Fr* __restrict__ scalars, size_t scalar_stride, const Fr* __r
             neg = 1;
             carry = 1;
         }
-        const bool valid = live && d != 0;
-        const uint32_t key = valid ? d - 1 : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, key);
-        const uint32_t leader = __ffs(peers) - 1, rank = __popc(peers & lt);
-        uint32_t pos = 0;
-        if (valid && lane == leader) pos = atomicAdd(base + key, (uint32_t)__popc(peers));
-        pos = __shfl_sync(0xffffffffu, pos, leader);
-        if (PASS == 1 && valid) entries[pos + rank] = ((uint32_t)j * n + i) | (neg << 31);
+        emit(mine && d != 0, d - 1, ((uint32_t)j * n + gi) | (neg << 31));
     }
 }
 
