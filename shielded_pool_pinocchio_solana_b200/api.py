@@ -4,6 +4,7 @@ Byte formats are gnark's (Fr 32 B BE, G1 64 B raw, G2 128 B raw), i.e. what
 `sunspot prove` reads and writes (/root/reference/client/proof.helper.ts:58-71).
 """
 import ctypes
+import os
 
 from . import _lib
 from ._lib import check
@@ -33,6 +34,7 @@ class Context:
     def comm_init(self, unique_id: bytes, rank, world):
         """Join the NCCL communicator of a single-proof-across-GPUs run (g16_comm_init)."""
         assert len(unique_id) == 128
+        _preload_nccl()
         check(self.lib.g16_comm_init(self.handle, unique_id, rank, world))
 
     def set_deferred_join(self, on=True):
@@ -224,8 +226,24 @@ def solve_assignment(ccs: bytes, assignment_be: bytes, nb_wires, blinder_be=None
     return wires.raw, committed.raw[:n_committed * 32]
 
 
+def _preload_nccl():
+    """Load the NCCL build PyTorch ships (nvidia-nccl wheel) before libg16b200 dlopens "libnccl.so.2": otherwise the
+    system NCCL would be bound first and a LATER `import torch` would resolve its newer symbols against it and fail."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations if spec else []):
+            path = os.path.join(root, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+                return
+    except Exception:                               # noqa: BLE001 -- fall back to the library's own search
+        pass
+
+
 def comm_unique_id() -> bytes:
     """NCCL unique id (rank 0 draws it, every rank passes it to Context.comm_init)."""
+    _preload_nccl()
     buf = ctypes.create_string_buffer(128)
     check(_lib.load().g16_comm_unique_id(buf))
     return buf.raw

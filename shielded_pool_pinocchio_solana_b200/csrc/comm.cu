@@ -7,7 +7,8 @@
 // and need no collective.
 //
 // NCCL is bound at run time (dlopen) so that single-GPU users of libg16b200.so do not need it installed;
-// in a torch process the already loaded libnccl.so.2 is reused.
+// in a torch process the already loaded libnccl.so.2 is reused (the Python mirror preloads the NCCL wheel that
+// PyTorch ships before the first g16_comm_* call, so that a later `import torch` finds its own build).
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -29,9 +30,14 @@ struct NcclApi {
 NcclApi& nccl() {
     static NcclApi api = [] {
         NcclApi a;
+        // 1. a libnccl the process already holds (e.g. the one bundled with PyTorch): two different NCCL builds in
+        //    one process resolve each other's symbols by SONAME and break whichever is loaded second
+        a.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        // 2. an explicit path, 3. the system library
+        if (!a.handle && getenv("G16_NCCL_LIB")) a.handle = dlopen(getenv("G16_NCCL_LIB"), RTLD_NOW | RTLD_LOCAL);
         for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-            a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
             if (a.handle) break;
+            a.handle = dlopen(name, RTLD_NOW | RTLD_LOCAL);
         }
         if (!a.handle) return a;
         a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.handle, "ncclGetUniqueId");

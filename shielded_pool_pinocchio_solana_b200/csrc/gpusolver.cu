@@ -252,7 +252,9 @@ k_solve_tpi(const uint32_t* __restrict__ lvl_off, const uint4* __restrict__ rec,
             if (inf.x == 0) {
                 if (L * Rr != O) atomicMin(e, inf.w + 1);           // constraint row (1-based)
             } else if (inf.x == 1) {
-                w[inf.y] = (L * Rr - O) * coeff_invs[inf.z];
+                // the defined wire almost always enters its row with coefficient +1 or -1: no division then
+                const Fr v = L * Rr - O;
+                w[inf.y] = (unit_ids && inf.z == 1) ? v : ((unit_ids && inf.z == 3) ? v.neg() : v * coeff_invs[inf.z]);
             } else if (inf.x == 2) {
                 // zero divisor: gnark leaves the wire at 0 and only checks the row (0 == O)
                 if (Rr.is_zero()) {
