@@ -50,6 +50,14 @@ struct g16_ctx {
     void* comm = nullptr;
     int rank = 0, world = 1;
     g16::DeviceBuf comm_recv;
+    // one large standalone MSM (g16_msm_dev, batch 1): point slices run as a software pipeline on MSM_PARTS streams
+    // (digit sort of one slice under the accumulation of another, bucket reduction tails hidden)
+    enum { MSM_PARTS = 4 };
+    g16::MsmRunner<g16::Fp> g1_part[MSM_PARTS];
+    g16::MsmRunner<g16::Fp2> g2_part[MSM_PARTS];
+    cudaStream_t part_stream[MSM_PARTS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t part_fork = nullptr, part_done[MSM_PARTS] = {nullptr, nullptr, nullptr, nullptr};
+    g16::DeviceBuf part_out;
     // g16_set_deferred_join: device-side calls (g16_prove_wires_dev) return without making the context stream wait
     // for their assembly; g16_join / g16_sync / the next use of the same buffers do.  Lets consecutive calls overlap.
     bool deferred_join = false;

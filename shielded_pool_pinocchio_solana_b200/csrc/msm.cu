@@ -106,7 +106,7 @@ void scan_u32(const uint32_t* in, size_t n, uint32_t* tile_sums, uint32_t* out, 
 template <class F>
 int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stride, const uint32_t* d_map,
                       int montgomery, size_t batch, Affine<F>* d_out, cudaStream_t st, const Fr* d_scalars1,
-                      size_t stride1) {
+                      size_t stride1, size_t lo, size_t cnt) {
     launches = 0;
     if (batch == 0) return G16_OK;
     if (!bases.table) {
@@ -114,9 +114,17 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
         return G16_E_ARG;
     }
     const MsmConfig cfg = bases.cfg;
-    const uint32_t n = (uint32_t)bases.n;
+    if (cnt == 0) {
+        lo = 0;
+        cnt = bases.n;
+    }
+    if (lo + cnt > bases.n) {
+        set_error("MsmRunner::run: point range out of bounds");
+        return G16_E_ARG;
+    }
+    const uint32_t n = (uint32_t)cnt, n_total = (uint32_t)bases.n;
     const size_t nbuckets = batch * cfg.nb;
-    const size_t nentries = batch * bases.n * cfg.W;   // upper bound (zero digits produce no entry)
+    const size_t nentries = batch * cnt * cfg.W;   // upper bound (zero digits produce no entry)
     if (nentries >= 4294967295.0 || nbuckets >= 2147483648.0) {
         set_error("MsmRunner: batch too large for 32-bit entry offsets");
         return G16_E_ARG;
@@ -125,7 +133,7 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     // A chain is at most `cap` additions long: ~2x the mean bucket size (Poisson tails stay unsplit),
     // so only the hot buckets of a skewed scalar vector are cut, into pieces that cost what a normal
     // bucket costs.
-    const double mean = (double)bases.n * cfg.W / cfg.nb;
+    const double mean = (double)cnt * cfg.W / cfg.nb;
     static const int ba_env = getenv("G16_MSM_BA") ? atoi(getenv("G16_MSM_BA")) : 0;
     static const int ba_cap = getenv("G16_BA_CAP") ? atoi(getenv("G16_BA_CAP")) : 16;
     const bool use_ba = ba_env != 0;
@@ -195,11 +203,11 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     if (prof) prof->mark(label, "begin", st);
     G16_CUDA(cudaMemsetAsync(counts, 0, 4 * nbuckets, st));
     G16_CUDA(cudaMemsetAsync(tab, 0, 4 * (2 * VB_CLASSES + 8), st));
-    k_msm_digits<0><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery, cfg,
-                                                         counts, nullptr);
+    k_msm_digits<0><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, (uint32_t)lo, n_total,
+                                                         montgomery, cfg, counts, nullptr);
     scan_u32(counts, nbuckets, tiles, starts, counts, st);
-    k_msm_digits<1><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, montgomery, cfg,
-                                                         counts, entries);
+    k_msm_digits<1><<<dgrid, MSM_DIGIT_THREADS, 0, st>>>(d_scalars, stride, d_scalars1, stride1, d_map, n, (uint32_t)lo, n_total,
+                                                         montgomery, cfg, counts, entries);
     // after the scatter, counts[k] (the cursor) is the END of bucket k
     // ---- virtual buckets, size classes, schedule -------------------------------------------------------
     k_vb_count<<<cdiv(nbuckets + 1, MSM_VB_THREADS), MSM_VB_THREADS, 0, st>>>(starts, counts, (uint32_t)nbuckets, cap, nv);

@@ -70,7 +70,7 @@ constexpr int MSM_DIGIT_THREADS = 256;
 template <int PASS>
 __global__ void __launch_bounds__(MSM_DIGIT_THREADS)
 k_msm_digits(const Fr* __restrict__ scalars, size_t scalar_stride, const Fr* __restrict__ scalars1,
-             size_t scalar_stride1, const uint32_t* __restrict__ map, uint32_t n,
+             size_t scalar_stride1, const uint32_t* __restrict__ map, uint32_t n, uint32_t lo, uint32_t n_total,
              int montgomery, MsmConfig cfg, uint32_t* __restrict__ counts_or_cursor,
              uint32_t* __restrict__ entries) {
     __shared__ uint32_t sk[8][MSM_DIGIT_THREADS];
@@ -83,7 +83,7 @@ k_msm_digits(const Fr* __restrict__ scalars, size_t scalar_stride, const Fr* __r
     Fr k = Fr::zero();
     if (live) {
         // map entries with bit 31 set read the second scalar source (e.g. the quotient H next to the wires)
-        uint32_t si = map ? map[i] : i;
+        uint32_t si = map ? map[lo + i] : lo + i;   // this launch covers points [lo, lo + n) of n_total
         k = (si >> 31) ? scalars1[(size_t)b * scalar_stride1 + (si & 0x7fffffffu)]
                        : scalars[(size_t)b * scalar_stride + si];
         // most wires of a real witness are 0 or 1: skip the Montgomery reduction for those
@@ -106,7 +106,7 @@ k_msm_digits(const Fr* __restrict__ scalars, size_t scalar_stride, const Fr* __r
     };
     // ---- scalars below 2^(c-1) (zero, one, bytes: ~90 % of a witness) have a single digit, in window 0 ----------
     const bool small = (k.v[1] | k.v[2] | k.v[3] | k.v[4] | k.v[5] | k.v[6] | k.v[7]) == 0 && k.v[0] <= half;
-    emit(live && small && k.v[0] != 0, k.v[0] - 1, i);
+    emit(live && small && k.v[0] != 0, k.v[0] - 1, lo + i);
     // ---- the others are compacted and walked window by window by full warps ---------------------------------------
     __syncthreads();
     if (live && !small) big_list[atomicAdd(&big_count, 1u)] = threadIdx.x;
@@ -115,7 +115,7 @@ k_msm_digits(const Fr* __restrict__ scalars, size_t scalar_stride, const Fr* __r
     if ((threadIdx.x & ~31u) >= nbig) return;   // whole warp idle
     const bool mine = threadIdx.x < nbig;
     const uint32_t src = mine ? big_list[threadIdx.x] : 0;
-    const uint32_t gi = blockIdx.x * MSM_DIGIT_THREADS + src;
+    const uint32_t gi = lo + blockIdx.x * MSM_DIGIT_THREADS + src;
     const uint32_t* s = &sk[0][src];
     uint32_t carry = 0;
     for (int j = 0; j < cfg.W; j++) {
@@ -131,7 +131,7 @@ k_msm_digits(const Fr* __restrict__ scalars, size_t scalar_stride, const Fr* __r
             neg = 1;
             carry = 1;
         }
-        emit(mine && d != 0, d - 1, ((uint32_t)j * n + gi) | (neg << 31));
+        emit(mine && d != 0, d - 1, ((uint32_t)j * n_total + gi) | (neg << 31));
     }
 }
 
@@ -670,8 +670,11 @@ class MsmRunner {
     ~MsmRunner() { release(); }
     // Computes out[b] = sum_i scalars[b*stride + map[i]] * P_i  for b < batch.  `out` is a DEVICE
     // array of `batch` affine points (Montgomery).  All work is enqueued on `st`.
+    // `lo`, `cnt` (cnt != 0): only the points [lo, lo + cnt) of the bases take part (a slice of one large MSM;
+    // slices run as a software pipeline on several streams, see g16_msm_dev).
     int run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stride, const uint32_t* d_map, int montgomery,
-            size_t batch, Affine<F>* d_out, cudaStream_t st, const Fr* d_scalars1 = nullptr, size_t stride1 = 0);
+            size_t batch, Affine<F>* d_out, cudaStream_t st, const Fr* d_scalars1 = nullptr, size_t stride1 = 0,
+            size_t lo = 0, size_t cnt = 0);
     void release();
     // kernels launched by the last run() (for bench.py's gpu_launches)
     int launches = 0;

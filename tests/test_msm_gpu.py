@@ -91,3 +91,33 @@ def test_point_range_split_and_combine(ctx, group):
     # an all-zero shard contributes the point at infinity
     inf = b"\x00" * size
     assert combine_partials(ctx, partials + [inf], group).hex() == case["results"][:2 * size]
+
+
+@pytest.mark.parametrize("group", ["g1", "g2"])
+def test_sliced_single_msm_matches_golden(ctx, group, monkeypatch):
+    """One large standalone MSM runs as 4 point slices pipelined on 4 streams (g16_msm_dev, >= 2^20 points): forced
+    here on the golden vectors (300 / 96 points incl. infinities, repeated and all-equal points), same bytes."""
+    import numpy as np
+    import torch
+    case = json.load(open(GOLDEN))[group]
+    n = len(bytes.fromhex(case["points"])) // (64 if group == "g1" else 128)
+    bases = ctx.load_bases(bytes.fromhex(case["points"]), group, window=0, batch_hint=1)
+    sc_be = bytes.fromhex(case["scalars"])[:32 * n]                       # first batch element
+    want = bases.msm(sc_be, batch=1)
+    limbs = np.frombuffer(sc_be, dtype=">u4").reshape(n, 8)[:, ::-1].astype(np.uint32)
+    d_sc = torch.from_numpy(np.ascontiguousarray(limbs).view(np.int32)).cuda()
+    out = torch.zeros(64 if group == "g2" else 32, dtype=torch.int32, device="cuda")
+    monkeypatch.setenv("G16_MSM_SLICE_MIN", "16")
+    torch.cuda.synchronize()
+    bases.msm_dev(d_sc.data_ptr(), 1, out.data_ptr(), montgomery=False)
+    ctx.sync()
+    torch.cuda.synchronize()
+    got_mont = out.cpu().numpy().view(np.uint32)
+    monkeypatch.setenv("G16_MSM_SLICE_MIN", "0")
+    out2 = torch.zeros_like(out)
+    bases.msm_dev(d_sc.data_ptr(), 1, out2.data_ptr(), montgomery=False)
+    ctx.sync()
+    torch.cuda.synchronize()
+    assert (got_mont == out2.cpu().numpy().view(np.uint32)).all()          # sliced == unsliced (Montgomery limbs)
+    assert want == bytes.fromhex(case["results"])[:len(want)]
+    bases.free()
