@@ -4,20 +4,29 @@
 namespace g16 {
 
 constexpr int NTT_THREADS = 256;
+#ifndef NTT_MIN_CTAS
+#define NTT_MIN_CTAS 2   // 3 (80 registers, spills) measured 3 % slower: the wide-multiplier dependency chains are the limit
+#endif
 constexpr int NTT_TILE_LOG = 11;  // 2048 elements = 64 KiB of shared memory per CTA
 constexpr int NTT_KC = 7;         // stages owned by the contiguous pass
 constexpr int NTT_KMAX = 8;       // max stages per strided pass
 
 // ---- shared-memory tile, limb-major ---------------------------------------------------------
+// One padding word per 32 positions: the butterflies of a stage touch positions 2^s (radix 2) or 4 * 2^s (radix 4)
+// apart, which without padding lands 2-8 lanes of a warp on the same bank (ncu, round 2: 1.4 conflicts per request
+// in the contiguous pass).
+__host__ __device__ __forceinline__ int tile_words(int T) { return T + (T >> 5); }
 __device__ __forceinline__ Fr tile_ld(const uint32_t* sm, int T, int pos) {
     Fr r;
+    const int TP = tile_words(T), pp = pos + (pos >> 5);
 #pragma unroll
-    for (int l = 0; l < 8; l++) r.v[l] = sm[l * T + pos];
+    for (int l = 0; l < 8; l++) r.v[l] = sm[l * TP + pp];
     return r;
 }
 __device__ __forceinline__ void tile_st(uint32_t* sm, int T, int pos, const Fr& x) {
+    const int TP = tile_words(T), pp = pos + (pos >> 5);
 #pragma unroll
-    for (int l = 0; l < 8; l++) sm[l * T + pos] = x.v[l];
+    for (int l = 0; l < 8; l++) sm[l * TP + pp] = x.v[l];
 }
 
 template <bool DIT>
@@ -33,9 +42,31 @@ __device__ __forceinline__ void butterfly(uint32_t* sm, int T, int p0, int p1, c
     }
 }
 
+// Two stages at once on four elements held in registers (radix 4): halves the shared-memory round trips and the
+// barriers of a pass.  p0 = position of the element whose bits `lo` and `hi = lo + 1` (of the tile-local row index)
+// are both clear, d1 / d2 = position strides of those bits; wA, wB = stage-hi twiddles of the pairs (e0,e2) / (e1,e3),
+// wC = stage-lo twiddle (shared by both of its pairs).  DIF runs stage hi first, DIT stage lo first.
+template <bool DIT>
+__device__ __forceinline__ void quad(uint32_t* sm, int T, int p0, int d1, int d2, const Fr& wA, const Fr& wB, const Fr& wC) {
+    Fr e0 = tile_ld(sm, T, p0), e1 = tile_ld(sm, T, p0 + d1), e2 = tile_ld(sm, T, p0 + d2), e3 = tile_ld(sm, T, p0 + d1 + d2);
+    if (DIT) {
+        Fr t1 = e1 * wC, t3 = e3 * wC;
+        Fr a0 = e0 + t1, a1 = e0 - t1, a2 = e2 + t3, a3 = e2 - t3;
+        Fr u2 = a2 * wA, u3 = a3 * wB;
+        e0 = a0 + u2; e2 = a0 - u2; e1 = a1 + u3; e3 = a1 - u3;
+    } else {
+        Fr a0 = e0 + e2, a2 = (e0 - e2) * wA, a1 = e1 + e3, a3 = (e1 - e3) * wB;
+        e0 = a0 + a1; e1 = (a0 - a1) * wC; e2 = a2 + a3; e3 = (a2 - a3) * wC;
+    }
+    tile_st(sm, T, p0, e0);
+    tile_st(sm, T, p0 + d1, e1);
+    tile_st(sm, T, p0 + d2, e2);
+    tile_st(sm, T, p0 + d1 + d2, e3);
+}
+
 // Strided pass: stages s_lo..s_hi (s_lo >= logC).  Tile = 2^k rows x C contiguous elements.
 template <bool DIT>
-__global__ void __launch_bounds__(NTT_THREADS)
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_CTAS)
 k_ntt_strided(Fr* __restrict__ data, size_t vec_stride, unsigned logn, int s_hi, int s_lo, int logC,
               const Fr* __restrict__ tw, const Fr* __restrict__ pre, const Fr* __restrict__ post) {
     extern __shared__ uint32_t sm[];
@@ -55,9 +86,8 @@ k_ntt_strided(Fr* __restrict__ data, size_t vec_stride, unsigned logn, int s_hi,
         tile_st(sm, T, e, v);
     }
     __syncthreads();
-    for (int st = 0; st < k; st++) {
-        const int s = DIT ? s_lo + st : s_hi - st;
-        const int ls = s - s_lo, hm = 1 << ls;
+    auto single = [&](int ls) {
+        const int s = s_lo + ls, hm = 1 << ls;
         for (int b = threadIdx.x; b < T / 2; b += NTT_THREADS) {
             int c = b & (C - 1), r = b >> logC;
             int m = ((r >> ls) << (ls + 1)) | (r & (hm - 1));
@@ -66,6 +96,29 @@ k_ntt_strided(Fr* __restrict__ data, size_t vec_stride, unsigned logn, int s_hi,
             butterfly<DIT>(sm, T, p0, p0 + (hm << logC), tw[j << (logn - 1 - s)]);
         }
         __syncthreads();
+    };
+    auto pair = [&](int lo) {   // tile-local stages lo and lo + 1
+        const int h1 = 1 << lo, hi = lo + 1, sh = s_lo + hi;
+        for (int q = threadIdx.x; q < T / 4; q += NTT_THREADS) {
+            int c = q & (C - 1), r = q >> logC;
+            int low = r & (h1 - 1);
+            int m0 = ((r >> lo) << (lo + 2)) | low;
+            size_t jlow = ((size_t)low << s_lo) | (lo0 + c);
+            const Fr wA = tw[jlow << (logn - 1 - sh)];
+            const Fr wB = tw[(jlow + ((size_t)h1 << s_lo)) << (logn - 1 - sh)];
+            const Fr wC = tw[jlow << (logn - sh)];
+            quad<DIT>(sm, T, (m0 << logC) | c, h1 << logC, (h1 << 1) << logC, wA, wB, wC);
+        }
+        __syncthreads();
+    };
+    if (DIT) {
+        int ls = 0;
+        for (; ls + 1 < k; ls += 2) pair(ls);
+        if (ls < k) single(ls);
+    } else {
+        int ls = k - 1;
+        for (; ls >= 1; ls -= 2) pair(ls - 1);
+        if (ls == 0) single(0);
     }
     for (int e = threadIdx.x; e < T; e += NTT_THREADS) {
         int m = e >> logC, c = e & (C - 1);
@@ -78,7 +131,7 @@ k_ntt_strided(Fr* __restrict__ data, size_t vec_stride, unsigned logn, int s_hi,
 
 // Contiguous pass: stages 0..k-1 on T = 2^logT adjacent elements (2^(logT-k) groups of 2^k).
 template <bool DIT>
-__global__ void __launch_bounds__(NTT_THREADS)
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_CTAS)
 k_ntt_contig(Fr* __restrict__ data, size_t vec_stride, unsigned logn, int k, int logT, const Fr* __restrict__ tw,
              const Fr* __restrict__ pre, const Fr* __restrict__ post) {
     extern __shared__ uint32_t sm[];
@@ -94,8 +147,7 @@ k_ntt_contig(Fr* __restrict__ data, size_t vec_stride, unsigned logn, int k, int
         tile_st(sm, T, e, v);
     }
     __syncthreads();
-    for (int st = 0; st < k; st++) {
-        const int s = DIT ? st : k - 1 - st;
+    auto single = [&](int s) {
         const int h = 1 << s;
         for (int b = threadIdx.x; b < T / 2; b += NTT_THREADS) {
             int r = b & ((1 << (k - 1)) - 1), g = b >> (k - 1);
@@ -105,6 +157,28 @@ k_ntt_contig(Fr* __restrict__ data, size_t vec_stride, unsigned logn, int k, int
             butterfly<DIT>(sm, T, p0, p0 + h, tw[j << (logn - 1 - s)]);
         }
         __syncthreads();
+    };
+    auto pair = [&](int lo) {   // stages lo and lo + 1 (k >= 2)
+        const int h1 = 1 << lo, sh = lo + 1;
+        for (int q = threadIdx.x; q < T / 4; q += NTT_THREADS) {
+            int r = q & ((1 << (k - 2)) - 1), g = q >> (k - 2);
+            int low = r & (h1 - 1);
+            int m0 = ((r >> lo) << (lo + 2)) | low;
+            const Fr wA = tw[(size_t)low << (logn - 1 - sh)];
+            const Fr wB = tw[(size_t)(low + h1) << (logn - 1 - sh)];
+            const Fr wC = tw[(size_t)low << (logn - sh)];
+            quad<DIT>(sm, T, (g << k) | m0, h1, h1 << 1, wA, wB, wC);
+        }
+        __syncthreads();
+    };
+    if (DIT) {
+        int ls = 0;
+        for (; ls + 1 < k; ls += 2) pair(ls);
+        if (ls < k) single(ls);
+    } else {
+        int ls = k - 1;
+        for (; ls >= 1; ls -= 2) pair(ls - 1);
+        if (ls == 0) single(0);
     }
     for (int e = threadIdx.x; e < T; e += NTT_THREADS) {
         Fr v = tile_ld(sm, T, e);
@@ -252,11 +326,15 @@ int NttEngine::run_strided(Fr* d_data, size_t vec_stride, unsigned logn, size_t 
     G16_TRY(domain(logn, st, &d));
     if (batch == 0) return G16_OK;
     if (!attr_done) {   // per engine = per context = per device (the attribute is per device)
-        int bytes = 32 << NTT_TILE_LOG;
+        int bytes = 32 * tile_words(1 << NTT_TILE_LOG);
         G16_CUDA(cudaFuncSetAttribute(k_ntt_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         G16_CUDA(cudaFuncSetAttribute(k_ntt_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         G16_CUDA(cudaFuncSetAttribute(k_ntt_contig<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         G16_CUDA(cudaFuncSetAttribute(k_ntt_contig<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        G16_CUDA(cudaFuncSetAttribute(k_ntt_strided<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        G16_CUDA(cudaFuncSetAttribute(k_ntt_strided<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        G16_CUDA(cudaFuncSetAttribute(k_ntt_contig<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        G16_CUDA(cudaFuncSetAttribute(k_ntt_contig<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_done = true;
     }
     Pass passes[8];
@@ -271,7 +349,7 @@ int NttEngine::run_strided(Fr* d_data, size_t vec_stride, unsigned logn, size_t 
             set_error("ntt: batch too large");
             return G16_E_ARG;
         }
-        size_t smem = (size_t)32 << p.logT;
+        size_t smem = (size_t)32 * tile_words(1 << p.logT);
         if (p.contig) {
             if (dir == NTT_DIF)
                 k_ntt_contig<false><<<(unsigned)tiles, NTT_THREADS, smem, st>>>(d_data, vec_stride, logn, p.s_hi + 1,
