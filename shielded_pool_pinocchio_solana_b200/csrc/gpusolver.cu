@@ -176,8 +176,15 @@ k_solve_levels(const uint32_t* __restrict__ lvl_off, const uint32_t* __restrict_
 // one thread per row the level costs the SUM of its terms' latencies.  Here SOLVE_TPI lanes share a row: each
 // takes every SOLVE_TPI-th term (descriptors, wires and coefficients of up to four terms are in flight
 // together), the partial sums of L, R and O meet through two xor-shuffles and the first lane finishes the row.
-constexpr int SOLVE_TPI = 4;
-constexpr int SOLVE_ROWS = SOLVE_THREADS / SOLVE_TPI;   // rows per pass of a CTA
+#ifndef SOLVE_TPI_LANES
+#define SOLVE_TPI_LANES 4
+#endif
+#ifndef SOLVE_TPI_THREADS
+#define SOLVE_TPI_THREADS 128
+#endif
+constexpr int SOLVE_TPI = SOLVE_TPI_LANES;
+constexpr int SOLVE_TT = SOLVE_TPI_THREADS;             // threads per proof of the term-parallel kernel
+constexpr int SOLVE_ROWS = SOLVE_TT / SOLVE_TPI;        // rows per pass of a CTA
 
 __device__ __forceinline__ Fr shfl_xor_fr(uint32_t mask, const Fr& a, int d) {
     Fr r;
@@ -191,7 +198,7 @@ __device__ __forceinline__ Fr shfl_xor_fr(uint32_t mask, const Fr& a, int d) {
 #ifndef SOLVE_MIN_CTAS
 #define SOLVE_MIN_CTAS 1
 #endif
-__global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MIN_CTAS)
+__global__ void __launch_bounds__(SOLVE_TT, SOLVE_MIN_CTAS)
 k_solve_tpi(const uint32_t* __restrict__ lvl_off, const uint4* __restrict__ rec, const uint32_t* __restrict__ calldata,
             const Fr* __restrict__ coeffs, const Fr* __restrict__ coeff_invs, Fr* wires, size_t wstride,
             size_t blinder_slot, uint32_t lvl_begin, uint32_t lvl_end, int unit_ids, uint32_t* err) {
@@ -487,7 +494,7 @@ int GpuSolverPlan::run(const Fr* d_coeffs, int unit_ids, Fr* d_wires, size_t wst
                                                               d_coeff_invs, d_wires, wstride, nw + X_BLINDER, lvl_begin,
                                                               lvl_end, unit_ids, d_err);
     else
-        k_solve_tpi<<<(unsigned)B, SOLVE_THREADS, 0, st>>>(d_lvl_off, d_rec, d_calldata, d_coeffs, d_coeff_invs, d_wires, wstride,
+        k_solve_tpi<<<(unsigned)B, SOLVE_TT, 0, st>>>(d_lvl_off, d_rec, d_calldata, d_coeffs, d_coeff_invs, d_wires, wstride,
                                                            nw + X_BLINDER, lvl_begin, lvl_end, unit_ids, d_err);
     G16_CUDA(cudaGetLastError());
     return G16_OK;
