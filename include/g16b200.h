@@ -145,6 +145,12 @@ int g16_setup(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uint8_t* s
  * public part).  *_len: in = capacity, out = bytes written. */
 int g16_prove(g16_circuit* c, const uint8_t* witness_gz, size_t witness_len, const uint8_t rnd[96],
               uint8_t* proof, size_t* proof_len, uint8_t* pw, size_t* pw_len);
+/* Host only (no GPU): the witness-ingest step alone -- Noir witness file (gzip of a WitnessStack: plain bincode, or a
+ * format byte followed by bincode / MessagePack, field elements as 32 raw bytes or 64 hex characters) -> the
+ * public + secret assignment of the circuit in `.ccs` order, 32 B big-endian each.  Two-call pattern: out = NULL
+ * returns the value count in *n_values. */
+int g16_witness_to_assignment(const uint8_t* ccs, size_t ccs_len, const uint8_t* witness_gz, size_t witness_len,
+                              uint8_t* assignment_be, size_t* n_values);
 /* Witness only: full wire vectors (n * nbWires * 32 B big-endian) for n assignments -- the R1CS
  * solve of gnark's Prove, with the BSB22 commitment MSM on the GPU.  rnd as in g16_prove_batch
  * (only the blinder is used). */

@@ -226,6 +226,16 @@ def solve_assignment(ccs: bytes, assignment_be: bytes, nb_wires, blinder_be=None
     return wires.raw, committed.raw[:n_committed * 32]
 
 
+def witness_to_assignment(ccs: bytes, witness_gz: bytes) -> bytes:
+    """Host only: Noir witness file -> public + secret assignment (32 B big-endian values, `.ccs` order)."""
+    lib = _lib.load()
+    n = ctypes.c_size_t(0)
+    check(lib.g16_witness_to_assignment(ccs, len(ccs), witness_gz, len(witness_gz), None, ctypes.byref(n)))
+    buf = ctypes.create_string_buffer(32 * n.value)
+    check(lib.g16_witness_to_assignment(ccs, len(ccs), witness_gz, len(witness_gz), buf, ctypes.byref(n)))
+    return buf.raw
+
+
 def _preload_nccl():
     """Load the NCCL build PyTorch ships (nvidia-nccl wheel) before libg16b200 dlopens "libnccl.so.2": otherwise the
     system NCCL would be bound first and a LATER `import torch` would resolve its newer symbols against it and fail."""

@@ -1284,6 +1284,28 @@ int g16_prove(g16_circuit* c, const uint8_t* witness_gz, size_t witness_len, con
     return g16_prove_assignment(c, asg.data(), asg.size() / 32, rnd, proof, proof_len, pw, pw_len);
 }
 
+int g16_witness_to_assignment(const uint8_t* ccs, size_t ccs_len, const uint8_t* witness_gz, size_t witness_len,
+                              uint8_t* assignment_be, size_t* n_values) {
+    if (!ccs || !witness_gz || !n_values) {
+        set_error("g16_witness_to_assignment: bad arguments");
+        return G16_E_ARG;
+    }
+    Circuit circ;
+    G16_TRY(parse_ccs(ccs, ccs_len, &circ));
+    std::vector<uint8_t> asg;
+    G16_TRY(witness_to_assignment(circ, witness_gz, witness_len, &asg));
+    const size_t n = asg.size() / 32;
+    if (assignment_be) {
+        if (*n_values < n) {
+            set_error("g16_witness_to_assignment: output buffer too small");
+            return G16_E_ARG;
+        }
+        memcpy(assignment_be, asg.data(), asg.size());
+    }
+    *n_values = n;
+    return G16_OK;
+}
+
 // Full wire vectors only (two-phase solve with the commitment MSM on the GPU), no proof.
 int g16_witness_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, size_t n_values, const uint8_t* rnd,
                       uint8_t* wires_be) {
