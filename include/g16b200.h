@@ -156,6 +156,10 @@ int g16_witness_to_assignment(const uint8_t* ccs, size_t ccs_len, const uint8_t*
  * (only the blinder is used). */
 int g16_witness_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, size_t n_values, const uint8_t* rnd,
                       uint8_t* wires_be);
+/* The same through the batched DEVICE solver (the one g16_prove_batch uses); G16_E_HINT when the circuit has to be
+ * solved on the host (g16_circuit_solver() says why). */
+int g16_witness_batch_dev(g16_circuit* c, size_t n, const uint8_t* assignments_be, size_t n_values, const uint8_t* rnd,
+                          uint8_t* wires_be);
 /* Same, from the public+secret assignment directly (32 B big-endian each, `.ccs` order:
  * Public[1..] then Secret[..]) -- skips the Noir container, runs the R1CS solver. */
 int g16_prove_assignment(g16_circuit* c, const uint8_t* assignment_be, size_t n_values, const uint8_t rnd[96],

@@ -209,6 +209,12 @@ class Circuit:
         check(self.ctx.lib.g16_witness_batch(self.handle, n, assignments_be, self.n_values, rnd, out))
         return out.raw
 
+    def witness_batch_dev(self, assignments_be: bytes, n, rnd: bytes = None) -> bytes:
+        """Full wire vectors from the batched DEVICE solver (G16Error code 4 when the circuit needs the host solver)."""
+        out = ctypes.create_string_buffer(n * self.info["nb_wires"] * 32)
+        check(self.ctx.lib.g16_witness_batch_dev(self.handle, n, assignments_be, self.n_values, rnd, out))
+        return out.raw
+
     def prove_wires_dev(self, d_wires_ptr, n, d_out_ptr, rnd: bytes = None):
         """Device-resident wires in, 320-byte proof points out (device); rnd = n*96 B or None (CSPRNG)."""
         assert rnd is None or len(rnd) == 96 * n

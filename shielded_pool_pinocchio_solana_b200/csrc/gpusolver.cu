@@ -317,6 +317,14 @@ k_assign(const uint8_t* __restrict__ asg_be, const uint8_t* __restrict__ rnd_be,
     }
 }
 
+__global__ void k_scatter_wires(Fr* wires, size_t wstride, const uint32_t* __restrict__ ids, const Fr* __restrict__ values,
+                                uint32_t nids, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nids * n) return;
+    uint32_t b = i / nids, k = i % nids;
+    wires[(size_t)b * wstride + ids[k]] = values[i];
+}
+
 __global__ void k_set_wire(Fr* wires, size_t wstride, uint32_t wire, const Fr* __restrict__ values, uint32_t n) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < n) wires[(size_t)b * wstride + wire] = values[b];
@@ -336,6 +344,10 @@ void GpuSolverPlan::release() {
     cudaFree(d_coeff_invs);
     cudaFree(d_rec);
     d_rec = nullptr;
+    cudaFree(d_host_wires);
+    d_host_wires = nullptr;
+    host_hints.clear();
+    host_wires.clear();
     d_lvl_off = d_lvl_instr = d_instr_cd = d_calldata = nullptr;
     d_info = nullptr;
     d_coeff_invs = nullptr;
@@ -345,8 +357,8 @@ void GpuSolverPlan::release() {
 int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not) {
     release();
     const uint32_t nw = c.nb_wires();
-    std::vector<uint8_t> known(nw, 0);
-    for (uint32_t i = 0; i < c.nb_public + c.nb_secret; i++) known[i] = 1;
+    std::vector<uint8_t> known(nw, 0), host_known(nw, 0);
+    for (uint32_t i = 0; i < c.nb_public + c.nb_secret; i++) known[i] = host_known[i] = 1;
     const size_t ninstr = c.blueprint.size();
     std::vector<uint4> info(ninstr, make_uint4(0, 0, 0, 0));
     std::vector<uint32_t> lvl_off(1, 0), lvl_instr, instr_cd(ninstr);
@@ -407,6 +419,28 @@ int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not
                     commit_wire = o0;
                     continue;   // executed by prove.cu between the two phases
                 }
+                if (kind == HINT_EMULATED_MUL || kind == HINT_GRUMPKIN_SPLIT || kind == HINT_GRUMPKIN_LIMBS) {
+                    // integer hints: host-evaluated up front when they hang off the inputs only
+                    bool from_inputs = true;
+                    size_t q = 3;
+                    for (uint32_t i = 0; i < nin && from_inputs; i++) {
+                        const uint32_t ln = cd[q++];
+                        for (uint32_t t = 0; t < ln; t++, q += 2)
+                            if (cd[q + 1] != CCS_CONST_WIRE && !host_known[cd[q + 1]]) from_inputs = false;
+                    }
+                    if (!from_inputs) {
+                        auto nm = c.hint_names.find(hid);
+                        *why_not = "integer hint fed by solved wires (host solver only): " + (nm == c.hint_names.end() ? std::to_string(hid) : nm->second);
+                        return G16_OK;
+                    }
+                    host_hints.push_back(ins);
+                    for (uint32_t wv = o0; wv < o1 && wv < nw; wv++) {
+                        host_wires.push_back(wv);
+                        host_known[wv] = 1;
+                        known[wv] = 1;   // in place before level 0 runs
+                    }
+                    continue;
+                }
                 if (kind == HINT_UNKNOWN) {
                     auto nm = c.hint_names.find(hid);
                     *why_not = "hint without a device implementation: " + (nm == c.hint_names.end() ? std::to_string(hid) : nm->second);
@@ -465,6 +499,7 @@ int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not
         rec[2 * k + 1] = c.blueprint[ins] == 1 ? make_uint4(instr_cd[ins], cd[1], cd[2], cd[3]) : make_uint4(instr_cd[ins], 0, 0, 0);
     }
     G16_TRY(upload(rec, &d_rec, st));
+    G16_TRY(upload(host_wires, &d_host_wires, st));
     G16_TRY(upload(lvl_off, &d_lvl_off, st));
     G16_TRY(upload(lvl_instr, &d_lvl_instr, st));
     G16_TRY(upload(info, &d_info, st));
@@ -496,6 +531,14 @@ int GpuSolverPlan::run(const Fr* d_coeffs, int unit_ids, Fr* d_wires, size_t wst
     else
         k_solve_tpi<<<(unsigned)B, SOLVE_TT, 0, st>>>(d_lvl_off, d_rec, d_calldata, d_coeffs, d_coeff_invs, d_wires, wstride,
                                                            nw + X_BLINDER, lvl_begin, lvl_end, unit_ids, d_err);
+    G16_CUDA(cudaGetLastError());
+    return G16_OK;
+}
+
+int GpuSolverPlan::scatter_host_wires(Fr* d_wires, size_t wstride, const Fr* d_values, size_t B, cudaStream_t st) const {
+    const size_t total = host_wires.size() * B;
+    if (!total) return G16_OK;
+    k_scatter_wires<<<cdiv(total, 256), 256, 0, st>>>(d_wires, wstride, d_host_wires, d_values, (uint32_t)host_wires.size(), (uint32_t)B);
     G16_CUDA(cudaGetLastError());
     return G16_OK;
 }

@@ -21,6 +21,12 @@ struct GpuSolverPlan {
     uint4* d_info = nullptr;
     uint4* d_rec = nullptr;                 // flattened plan: two uint4 per instruction, in level order
     Fr* d_coeff_invs = nullptr;
+    // Hints that work over the integers (emulated.mulHint, the sw-grumpkin scalar split) have no device version; when
+    // their inputs only depend on the circuit's inputs (and on each other) the host evaluates them per proof before
+    // the device solve and their outputs are scattered into the wire vectors like extra inputs.
+    std::vector<uint32_t> host_hints;   // instruction ids, in dependency order
+    std::vector<uint32_t> host_wires;   // their output wires, concatenated
+    uint32_t* d_host_wires = nullptr;
 
     // Compiles the plan; leaves valid == false (and says why) when the circuit needs the host solver.
     int build(const Circuit& c, cudaStream_t st, std::string* why_not);
@@ -30,6 +36,8 @@ struct GpuSolverPlan {
     int run(const Fr* d_coeffs, int unit_ids, Fr* d_wires, size_t wstride, size_t nw, size_t B, uint32_t lvl_begin,
             uint32_t lvl_end, uint32_t* d_err, cudaStream_t st) const;
     int set_wire(Fr* d_wires, size_t wstride, uint32_t wire, const Fr* d_values, size_t B, cudaStream_t st) const;
+    // d_values[b * host_wires.size() + i] -> wire host_wires[i] of proof b
+    int scatter_host_wires(Fr* d_wires, size_t wstride, const Fr* d_values, size_t B, cudaStream_t st) const;
     void release();
     ~GpuSolverPlan() { release(); }
 };

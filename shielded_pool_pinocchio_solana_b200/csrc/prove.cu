@@ -984,7 +984,7 @@ static StageResult stage_solve(g16_circuit* c, int slot_id, size_t B, const uint
 
 // ---- stage A on the GPU: assignments -> full wire vectors in slot.d_wires (gpusolver.cu) ------------
 static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const uint8_t* assignments_be,
-                                   const uint8_t* rnd, size_t first_index) {
+                                   const uint8_t* rnd, size_t first_index, bool tolerate = false) {
     StageResult res;
     auto failm = [&](int rc, const std::string& m) {
         res.rc = rc;
@@ -1022,6 +1022,37 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
     G16_STAGE_CUDA(cudaMemsetAsync(d_err, 0xff, 4 * B, st));
     int rc = c->plan.assign((const uint8_t*)sl.d_asg_be.ptr, (const uint8_t*)sl.d_rnd_be.ptr, (uint32_t)nin, W, c->wstride, c->nw, B, st);
     if (rc != G16_OK) return failm(rc, get_error());
+    if (!c->plan.host_hints.empty()) {
+        // integer hints that hang off the inputs (withdraw circuit: the Grumpkin scalar split and its emulated product
+        // check): evaluated on the host per proof, scattered into the device wire vectors before level 0
+        const size_t npre = c->plan.host_wires.size();
+        std::vector<HFr> pre(npre * B);
+        std::vector<int> rcs(B, G16_OK);
+        std::vector<std::string> errs(B);
+        const size_t workers = std::min<size_t>(default_threads(), B);
+        parallel_for(workers, [&](size_t t) {
+            SolveState stt;
+            std::vector<HFr> asg(nin);
+            for (size_t b = t; b < B; b += workers) {
+                const uint8_t* src = assignments_be + b * nin * 32;
+                for (size_t i = 0; i < nin; i++) asg[i] = HFr::from_be(src + 32 * i);
+                solve_begin(circ, asg.data(), &stt);
+                stt.tolerate = tolerate;
+                for (uint32_t ins : c->plan.host_hints)
+                    if ((rcs[b] = solve_run_hint(circ, &stt, ins)) != G16_OK) {
+                        errs[b] = stt.error;
+                        break;
+                    }
+                for (size_t k = 0; k < npre; k++) pre[b * npre + k] = stt.w[c->plan.host_wires[k]];
+            }
+        });
+        for (size_t b = 0; b < B; b++)
+            if (rcs[b] != G16_OK && !tolerate) return failm(rcs[b], "proof " + std::to_string(first_index + b) + ": " + errs[b]);
+        if (sl.d_pre.ensure(sizeof(Fr) * npre * B) != G16_OK) return failm(G16_E_CUDA, get_error());
+        G16_STAGE_CUDA(cudaMemcpyAsync(sl.d_pre.ptr, pre.data(), sizeof(Fr) * npre * B, cudaMemcpyHostToDevice, st));
+        G16_STAGE_CUDA(cudaStreamSynchronize(st));   // `pre` is pageable and dies with this scope
+        if ((rc = c->plan.scatter_host_wires(W, c->wstride, (const Fr*)sl.d_pre.ptr, B, st)) != G16_OK) return failm(rc, get_error());
+    }
     const bool commit = c->plan.commit_level != (uint32_t)-1;
     const uint32_t split = commit ? c->plan.commit_level + 1 : c->plan.nlevels;
     if ((rc = c->plan.run(c->d_coeffs, c->unit_ids, W, c->wstride, c->nw, B, 0, split, d_err, st)) != G16_OK) return failm(rc, get_error());
@@ -1049,7 +1080,7 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
     G16_STAGE_CUDA(cudaEventRecord(sl.ready, st));
     G16_STAGE_CUDA(cudaStreamSynchronize(st));
     trace("solve_gpu: done");
-    for (size_t b = 0; b < B; b++)
+    for (size_t b = 0; b < B && !tolerate; b++)
         if (h_err[b] != 0xffffffffu) {
             if (h_err[b] & 0x80000000u) return failm(G16_E_HINT, "proof " + std::to_string(first_index + b) + ": solver hint failed on the device");
             return failm(G16_E_UNSAT, "proof " + std::to_string(first_index + b) + ": constraint #" + std::to_string(h_err[b] - 1) + " is not satisfied");
@@ -1255,7 +1286,7 @@ int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, siz
         const size_t first = g * SB, G = std::min(SB, n - first);
         if (c->plan.valid)   // G16_SOLVE_OVERLAP=0 runs the device solver between groups instead of beside them
             return std::async(solve_overlap ? std::launch::async : std::launch::deferred, stage_solve_gpu, c, (int)(g & 1), G,
-                              assignments_be + first * nin * 32, rnd ? rnd + 96 * first : nullptr, first);
+                              assignments_be + first * nin * 32, rnd ? rnd + 96 * first : nullptr, first, false);
         return std::async(std::launch::async, stage_solve, c, (int)(g & 1), G, assignments_be + first * nin * 32,
                           rnd ? rnd + 96 * first : nullptr, first, true);
     };
@@ -1329,6 +1360,44 @@ int g16_witness_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, s
         const HFr* W = (const HFr*)c->slots[0].h_wires;
         parallel_for(B, [&](size_t b) {
             for (size_t i = 0; i < c->nw; i++) W[b * c->wstride + i].to_be(wires_be + ((done + b) * c->nw + i) * 32);
+        });
+        done += B;
+    }
+    return G16_OK;
+}
+
+// The same through the DEVICE solver (the one g16_prove_batch uses); fails with G16_E_HINT when the circuit has to be
+// solved on the host.  G16_SOLVER_DIAG=1: unsatisfied rows do not fail the call (tests).
+int g16_witness_batch_dev(g16_circuit* c, size_t n, const uint8_t* assignments_be, size_t n_values, const uint8_t* rnd,
+                          uint8_t* wires_be) {
+    if (!c || !assignments_be || !wires_be || n == 0) {
+        set_error("g16_witness_batch_dev: bad arguments");
+        return G16_E_ARG;
+    }
+    const size_t nin = c->circ.nb_public - 1 + c->circ.nb_secret;
+    if (n_values != nin) {
+        set_error("g16_witness_batch_dev: assignment size mismatch");
+        return G16_E_ARG;
+    }
+    if (!c->plan.valid) {
+        set_error("g16_witness_batch_dev: this circuit is solved on the host (" + c->host_solver_reason + ")");
+        return G16_E_HINT;
+    }
+    G16_CUDA(cudaSetDevice(c->ctx->device));
+    G16_LOCK(c->ctx);
+    const bool tolerate = getenv("G16_SOLVER_DIAG") && atoi(getenv("G16_SOLVER_DIAG")) != 0;
+    std::vector<HFr> w;
+    for (size_t done = 0; done < n;) {
+        const size_t B = std::min(c->solve_batch, n - done);
+        StageResult sr = stage_solve_gpu(c, 0, B, assignments_be + done * nin * 32, rnd ? rnd + 96 * done : nullptr, done, tolerate);
+        if (sr.rc != G16_OK) {
+            set_error(sr.err);
+            return sr.rc;
+        }
+        w.resize(c->wstride * B);
+        G16_CUDA(cudaMemcpy(w.data(), c->slots[0].d_wires.ptr, sizeof(Fr) * c->wstride * B, cudaMemcpyDeviceToHost));
+        parallel_for(B, [&](size_t b) {
+            for (size_t i = 0; i < c->nw; i++) w[b * c->wstride + i].to_be(wires_be + ((done + b) * c->nw + i) * 32);
         });
         done += B;
     }

@@ -81,6 +81,7 @@ struct g16_circuit {
     // k+1 into the other slot (its commitment MSM runs on `aux_stream` with its own MSM scratch).
     struct Slot {
         g16::DeviceBuf d_wires, d_commit_vals, d_commit_out, d_asg_be, d_rnd_be, d_err, d_chal;
+        g16::DeviceBuf d_pre;            // host-evaluated hint outputs (GpuSolverPlan::host_wires)
         g16::DeviceBuf d_wires_be;       // g16_prove_wires: the caller's big-endian wire vectors (grown on first use)
         void* h_stage = nullptr;         // pinned: assignments | rnd | challenges | err
         void* h_wires = nullptr;         // pinned, max_batch * wstride Fr

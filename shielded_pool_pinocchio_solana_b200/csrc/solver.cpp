@@ -127,8 +127,7 @@ int run_hint(const Circuit& c, SolveState* st, uint32_t instr, const HFr* blinde
                 auto it = index.find(key_of(q));
                 if (it == index.end()) {
                     if (!st->tolerate) return fail(st, G16_E_HINT, "countHint: query not in table");
-                    for (uint32_t k = 0; k < nout; k++) set_out(k, HFr::zero());
-                    return G16_OK;
+                    continue;   // diagnostic mode: count what is there (what the device solver does, too)
                 }
                 mult[it->second]++;
             }
@@ -368,6 +367,11 @@ int solve_run(const Circuit& c, SolveState* st, const HFr* blinder) {
     for (size_t i = 0; i < st->known.size(); i++)
         if (!st->known[i]) return fail(st, G16_E_UNSAT, "wire " + std::to_string(i) + " was never solved");
     return SOLVE_DONE;
+}
+
+int solve_run_hint(const Circuit& c, SolveState* st, uint32_t instr) {
+    bool paused = false;
+    return run_hint(c, st, instr, nullptr, &paused);
 }
 
 void solve_provide_challenge(SolveState* st, const HFr& challenge) {

@@ -38,5 +38,7 @@ void solve_begin(const Circuit& c, const HFr* assignment, SolveState* st);
 // returns SOLVE_DONE, SOLVE_NEED_COMMITMENT, or a G16_E_* code (st->error holds the message)
 int solve_run(const Circuit& c, SolveState* st, const HFr* blinder);
 void solve_provide_challenge(SolveState* st, const HFr& challenge);
+// one hint instruction on its own (the device solver's host-evaluated hints, gpusolver.cuh); G16_OK or a G16_E_* code
+int solve_run_hint(const Circuit& c, SolveState* st, uint32_t instr);
 
 }  // namespace g16

@@ -160,3 +160,47 @@ def test_real_withdraw_circuit_shape_on_gpu(ctx):
     for i in range(B):
         assert got[i] == orc.proof(wires[i * nw * 32:(i + 1) * nw * 32], rnd[96 * i:96 * i + 96]), "proof %d" % i
     circ.free()
+
+
+def test_device_solver_equals_host_solver_audit_like(audit):
+    """The batched device witness solver (k_solve_tpi, what g16_prove_batch uses) and the C++ host solver agree on
+    every wire of a full group of audit_like witnesses (two-phase solve, commitment MSM and challenge in between)."""
+    sc, circ, orc, vk = audit
+    n = 70                                              # more than one device batch, ragged
+    asg = b"".join(sc.assignment_bytes(9000 + i) for i in range(n))
+    rnd = b"".join(rnd_for(300 + i) for i in range(n))
+    assert circ.solver == "gpu"
+    assert circ.witness_batch_dev(asg, n, rnd) == circ.witness_batch(asg, n, rnd)
+
+
+def test_withdraw_circuit_solves_on_the_device(ctx, monkeypatch):
+    """The reference's withdraw circuit takes the DEVICE solver: its three integer hints (Grumpkin scalar split, limb
+    decomposition, emulated product) hang off an input wire, are evaluated on the host per proof and scattered into the
+    wire vectors before level 0.  No satisfying witness exists offline, so random inputs in diagnostic mode: every wire
+    must equal the host solver's (itself equal to oracle/py, tests/test_hints.py), given the same commitment challenge."""
+    import ccs as occs
+    raw = open(os.path.join(GOLD, "shielded_pool_verifier.ccs"), "rb").read()
+    c = occs.parse_ccs(raw)
+    pk, _vk = ctx.setup(raw, b"withdraw-device-solver")
+    circ = ctx.load_circuit(raw, pk)
+    assert circ.solver == "gpu", circ.solver
+    monkeypatch.setenv("G16_SOLVER_DIAG", "1")
+    rng = random.Random(17)
+    nin = c.nb_public - 1 + c.nb_secret
+    n = 3
+    asgs = []
+    for b in range(n):
+        a = [rng.randrange(R) for _ in range(nin)]
+        a[27] = rng.randrange(1 << 128) if b % 2 == 0 else rng.randrange(R)
+        asgs.append(b"".join(v.to_bytes(32, "big") for v in a))
+    rnd = b"".join(rnd_for(500 + i) for i in range(n))
+    dev = circ.witness_batch_dev(b"".join(asgs), n, rnd)
+    nwb = c.nb_wires * 32
+    cw = c.commitments[0]["CommitmentIndex"]
+    for b in range(n):
+        w_dev = dev[b * nwb:(b + 1) * nwb]
+        host, _ = g16.solve_assignment(raw, asgs[b], c.nb_wires, blinder_be=rnd[96 * b + 64:96 * b + 96],
+                                       challenges_be=w_dev[32 * cw:32 * cw + 32],
+                                       n_committed=len(c.commitments[0]["PrivateCommitted"]))
+        assert w_dev == host, "proof %d" % b
+    circ.free()
