@@ -204,3 +204,50 @@ def test_withdraw_circuit_solves_on_the_device(ctx, monkeypatch):
                                        n_committed=len(c.commitments[0]["PrivateCommitted"]))
         assert w_dev == host, "proof %d" % b
     circ.free()
+
+
+def test_withdraw_real_witnesses_prove_bit_exact_and_verify(ctx):
+    """BASELINE.json configs[0] on the GPU: the reference's withdraw circuit, REAL witnesses (tests/golden/
+    withdraw_assignments.bin: witness 0 = client/prover-params.toml), from assignments through the DEVICE solver
+    (host-evaluated integer hints), a ragged multi-chunk batch.  Proof bytes = oracle/c from the same wires and (r, s);
+    every proof passes the product's verifier and the oracle's pairing check; the .pw is the toml's five public inputs."""
+    import json
+    import groth16 as G
+    raw = open(os.path.join(GOLD, "shielded_pool_verifier.ccs"), "rb").read()
+    meta = json.load(open(os.path.join(GOLD, "withdraw_assignments.json")))
+    blob = open(os.path.join(GOLD, "withdraw_assignments.bin"), "rb").read()
+    nb = meta["n_values"] * 32
+    fixtures = [blob[i * nb:(i + 1) * nb] for i in range(meta["n"])]
+    pk, vk = ctx.setup(raw, b"withdraw-real-gpu")
+    circ = ctx.load_circuit(raw, pk)
+    assert circ.solver == "gpu" and circ.proof_len == 388 and circ.pw_len == 172
+    n = 70                                                   # two device chunks, the second ragged
+    asg = b"".join(fixtures[i % len(fixtures)] for i in range(n))
+    rnd = b"".join(rnd_for(700 + i) for i in range(n))
+    proofs, pws = circ.prove_batch(asg, n, rnd)
+    orc = Oracle(raw, pk)
+    wires = circ.witness_batch(asg[:len(fixtures) * nb], len(fixtures), rnd[:96 * len(fixtures)])     # host solver
+    nwb = orc.nw * 32
+    assert circ.witness_batch_dev(asg[:len(fixtures) * nb], len(fixtures), rnd[:96 * len(fixtures)]) == wires
+    for i in (0, 1, 2, 3):
+        assert proofs[i] == orc.proof(wires[i * nwb:(i + 1) * nwb], rnd[96 * i:96 * i + 96]), "proof %d" % i
+    ovk = G.read_vk(vk)
+    for i in (0, 3, 64, 69):
+        assert g16.verify(vk, proofs[i], pws[i]) and G.verify(ovk, proofs[i], pws[i]), "proof %d" % i
+    assert not g16.verify(vk, proofs[0], pws[1])             # another witness's public inputs
+    want = meta["prover_params_toml"]
+    assert pws[0] == bytes.fromhex("000000050000000000000005") + b"".join(
+        bytes.fromhex(want[k]) for k in ("root", "nullifier", "recipient", "amount", "wa_commitment"))
+    # the witness-file front door: the full ACIR witness map, as `nargo execute` writes it
+    import gzip
+    import struct
+    import ccs as occs
+    c = occs.parse_ccs(raw)
+    secret = [int(name.rsplit("_", 1)[1]) for name in c.body["Secret"]]
+    vals = [fixtures[0][32 * i:32 * i + 32] for i in range(meta["n_values"])]
+    acir = {k: vals[k] for k in range(5)}
+    acir.update({k: vals[5 + pos] for pos, k in enumerate(secret)})
+    body = struct.pack("<QIQ", 1, 0, len(acir)) + b"".join(struct.pack("<IQ", k, 32) + v for k, v in sorted(acir.items()))
+    p0, w0 = circ.prove(gzip.compress(body), rnd[:96])
+    assert p0 == proofs[0] and w0 == pws[0]
+    circ.free()

@@ -1,0 +1,101 @@
+"""The reference's withdraw circuit with REAL witnesses (BASELINE.json configs[0]).
+
+No witness file exists in the reference tree and there is no ACVM here, but the circuit's R1CS determines its own
+intermediate witnesses: oracle/py/witness_completion.py rebuilds a satisfying assignment from the ABI inputs of
+/root/reference/client/prover-params.toml (committed copy: tests/golden/prover-params.toml).  Given only the PRIVATE
+inputs it re-derives that file's public key and public inputs -- a known-answer test, on the reference's own vector,
+of the `.ccs` decoder, the solver semantics and the three sunspot / gnark integer hints.  CPU only."""
+import json
+import os
+import re
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "py"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import ccs as occs                                   # noqa: E402
+import groth16 as G                                  # noqa: E402
+import gen_golden_withdraw_witness as gen            # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+R = G.R
+
+
+@pytest.fixture(scope="module")
+def circuit():
+    return occs.parse_ccs(open(os.path.join(GOLD, "shielded_pool_verifier.ccs"), "rb").read())
+
+
+@pytest.fixture(scope="module")
+def fixtures():
+    meta = json.load(open(os.path.join(GOLD, "withdraw_assignments.json")))
+    blob = open(os.path.join(GOLD, "withdraw_assignments.bin"), "rb").read()
+    nb = meta["n_values"] * 32
+    return meta, [blob[i * nb:(i + 1) * nb] for i in range(meta["n"])]
+
+
+def toml_values():
+    txt = open(os.path.join(GOLD, "prover-params.toml")).read()
+    val = lambda k: int(re.search(r"^%s\s*=\s*\"?(0x[0-9a-f]+|\d+)\"?" % k, txt, re.M).group(1), 0)   # noqa: E731
+    out = {k: val(k) for k in ("root", "nullifier", "recipient", "amount", "wa_commitment", "secret_key", "owner_x",
+                               "owner_y", "randomness", "index")}
+    sib = re.findall(r"\"(0x[0-9a-f]{64})\",", txt.split("siblings", 1)[1])
+    assert len(sib) == 16
+    for i, s in enumerate(sib):
+        out["sibling_%d" % i] = int(s, 16)
+    return out
+
+
+def test_private_inputs_of_prover_params_rederive_its_public_inputs(circuit, fixtures):
+    """secret_key, randomness, index, siblings (+ recipient, amount) -> owner_x, owner_y = secret_key * G on Grumpkin
+    (sunspot's scalar-mul gadget driven by this repo's sw-grumpkin / emulated hints), wa_commitment, nullifier and the
+    Merkle root (Poseidon, as constraints) -- all equal to what the reference committed."""
+    want = toml_values()
+    inputs = {k: v for k, v in want.items() if k not in gen.DERIVED}
+    w, asg = gen.complete_from_private(circuit, inputs)
+    wmap = gen.wire_of_abi(circuit)
+    for k, name in enumerate(gen.ABI):
+        assert w[wmap[k]] == want[name], name
+    meta, blobs = fixtures
+    assert b"".join(v.to_bytes(32, "big") for v in asg) == blobs[0]          # the committed fixture is this assignment
+    assert {k: int(v, 16) for k, v in meta["prover_params_toml"].items()} == want
+    # the public witness file the on-chain program reads (withdraw.rs:14-16) is these five values
+    pw = G.write_public_witness([want[k] for k in ("root", "nullifier", "recipient", "amount", "wa_commitment")])
+    assert pw[12:] == blobs[0][:160]
+
+
+def test_fixture_witnesses_satisfy_every_row_and_both_solvers_agree(circuit, fixtures):
+    """Strict gnark-order solve (oracle/py) of every committed assignment; the product's C++ host solver gives the same
+    wires (commitment challenge injected)."""
+    import shielded_pool_pinocchio_solana_b200 as g16
+    meta, blobs = fixtures
+    raw = open(os.path.join(GOLD, "shielded_pool_verifier.ccs"), "rb").read()
+    pk, _vk, _ = G.setup(circuit, b"withdraw-real", fast=True)
+    cw = circuit.commitments[0]["CommitmentIndex"]
+    for n, blob in enumerate(blobs):
+        asg = [int.from_bytes(blob[32 * i:32 * i + 32], "big") for i in range(meta["n_values"])]
+        wires, _ = G.solve(circuit, asg, pk=pk, blinder=7 + n)
+        if n < 2:
+            for L, Rr, O in circuit.rows():
+                ev = lambda e: sum(circuit.coeffs[cid] * (1 if wid == occs.CONST_WIRE else wires[wid]) for cid, wid in e) % R   # noqa: E731
+                assert ev(L) * ev(Rr) % R == ev(O)
+        got, _ = g16.solve_assignment(raw, blob, circuit.nb_wires, blinder_be=(7 + n).to_bytes(32, "big"),
+                                      challenges_be=wires[cw].to_bytes(32, "big"),
+                                      n_committed=len(circuit.commitments[0]["PrivateCommitted"]))
+        assert got == b"".join(v.to_bytes(32, "big") for v in wires), "witness %d" % n
+    # distinct witnesses, and a real witness is dominated by full-size field elements (Poseidon), not by zeros and ones
+    assert len(set(blobs)) == len(blobs)
+    big = sum(1 for v in wires if v >> 128) / len(wires)
+    assert big > 0.85
+
+
+def test_a_wrong_private_input_is_rejected(circuit, fixtures):
+    meta, blobs = fixtures
+    asg = [int.from_bytes(blobs[0][32 * i:32 * i + 32], "big") for i in range(meta["n_values"])]
+    asg[5] ^= 1                                        # secret_key
+    pk, _vk, _ = G.setup(circuit, b"withdraw-real", fast=True)
+    with pytest.raises(G.Unsatisfied):
+        G.solve(circuit, asg, pk=pk, blinder=1)
