@@ -8,17 +8,18 @@ Workload = BASELINE.json configs[2] (the configuration the proofs/s metric is qu
 withdraw + audit proof PAIRS, sharded one-proof-per-GPU-slot, no data-path collective (weak scaling).
   * withdraw : the reference's own constraint system (tests/golden/shielded_pool_verifier.ccs = /root/reference/
                noir_circuit/target/shielded_pool_verifier.ccs: 12,452 rows, domain 2^14, MSM sizes 4,175 / 12,701 /
-               12,442 / 16,383 / 490), proved from full wire vectors drawn from the witness-like mix of SURVEY.md
-               8(d) (40 % zero, 30 % one, 20 % < 2^8, 10 % uniform): the circuit's three sunspot-private hints are
-               only needed to SOLVE it, the proving work is identical.
+               12,442 / 16,383 / 490) with REAL witnesses (tests/golden/withdraw_assignments.bin: witness 0 =
+               client/prover-params.toml, three more from seeded private inputs; tests/gen_golden_withdraw_witness.py).
+               A real withdraw witness is 92 % full-size field elements (Poseidon), i.e. the worst case for the MSMs,
+               not the witness-like mix SURVEY.md 8(d) assumed before a witness existed.
   * audit    : `audit_like` (26,000 rows, domain 2^15, 2 public inputs, 1 BSB22 commitment) -- the audit circuit's
                own .ccs/.pk are missing blobs in the reference.
 One step = one device batch per circuit = 64 pairs = 128 proofs; 4096 pairs = 64 steps (--steps 64).
 
  value : proofs/s, wire vectors already resident in HBM (g16_prove_wires_dev, non-zero blinding)
- e2e   : proofs/s through the reference-facing calls with HOST buffers inside the timed region: withdraw via
-         g16_prove_wires (host big-endian wires -> H2D), audit via g16_prove_batch (host assignments -> device
-         witness solver -> commitment -> proof), proof bytes back on the host
+ e2e   : proofs/s through the reference-facing call with HOST buffers inside the timed region: g16_prove_batch for
+         both circuits (host assignments -> H2D -> device witness solver -> commitment -> proof), proof bytes back on
+         the host
  roofline : the dominant kernel k_msm_accumulate (G1 + G2), CUDA events on the launching stream; integer-pipe
          bound; work = SURVEY.md 8(d): 23,936 IMAD per G1 point, 71,808 per G2 point; peak = this run's own
          IMAD microbenchmark (MEASURED_PEAKS.json has no integer number)
@@ -42,7 +43,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "groth16_proofs_per_sec"
 UNIT = "proofs/s"
-WORKLOAD = ("pairs: withdraw (reference shielded_pool_verifier.ccs, 12452 constraints, domain 2^14, witness-like wires) + "
+WORKLOAD = ("pairs: withdraw (reference shielded_pool_verifier.ccs, 12452 constraints, domain 2^14, REAL witnesses) + "
             "audit_like (26000 constraints, domain 2^15, 2 public inputs, 1 BSB22 commitment) -- BASELINE.json configs[2]; "
             "one step = 64 pairs per GPU")
 IMAD_PER_G1_POINT = 23936.0   # 16 windows x 11 modmul x 136 IMAD
@@ -128,6 +129,15 @@ def witness_like_wires(n_vectors, nw, seed):
     return np.ascontiguousarray(limbs[:, ::-1]).astype(">u4").tobytes()
 
 
+def withdraw_assignments(n, rotate=0):
+    """n real withdraw assignments (the committed fixtures, tiled), big-endian."""
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "withdraw_assignments.json")))
+    blob = open(os.path.join(ROOT, "tests", "golden", "withdraw_assignments.bin"), "rb").read()
+    nb = meta["n_values"] * 32
+    fx = [blob[i * nb:(i + 1) * nb] for i in range(meta["n"])]
+    return b"".join(fx[(i + rotate) % len(fx)] for i in range(n)), meta["n_values"]
+
+
 def bench_rnd(tag, n):
     return b"".join(hashlib.sha256(b"g16b200/bench/%s/%d" % (tag, k)).digest()[:31].rjust(32, b"\0") for k in range(3 * n))
 
@@ -182,9 +192,19 @@ class CpuProver:
         for k, (name, ccs_bytes, pk_bytes) in enumerate(workload):
             c = occs.parse_ccs(ccs_bytes)
             cc = coracle.CCircuit(c, G.read_pk(pk_bytes, c))
-            wires = witness_like_wires(4, c.nb_wires, 77 + k)
             nb = c.nb_wires * 32
-            self.items.append((cc, [wires[i * nb:(i + 1) * nb] for i in range(4)]))
+            if name == "withdraw":      # real witnesses, solved by the oracle's own solver
+                asg, nv = withdraw_assignments(4)
+                pk = G.read_pk(pk_bytes, c)
+                wl = []
+                for i in range(4):
+                    vals = [int.from_bytes(asg[(i * nv + j) * 32:(i * nv + j + 1) * 32], "big") for j in range(nv)]
+                    w, _ = G.solve(c, vals, pk=pk, blinder=1 + i)
+                    wl.append(b"".join(v.to_bytes(32, "big") for v in w))
+            else:
+                wires = witness_like_wires(4, c.nb_wires, 77 + k)
+                wl = [wires[i * nb:(i + 1) * nb] for i in range(4)]
+            self.items.append((cc, wl))
         self.k = 0
 
     def prove_pair(self):
@@ -247,7 +267,7 @@ def run_reference(args):
     value = max(latency_rate, sustained_rate)
     sample = ("latency mode: %d proofs in %.1f s with all %d threads on one proof at a time (%.2f proofs/s); sustained mode: "
               "%d proofs in %.1f s with one single-threaded prover per core (%.2f proofs/s); prove-from-wires "
-              "(SpMV, H, 6 MSMs) of withdraw + audit_like pairs, witness solve excluded; gnark-algorithm CPU "
+              "(SpMV, H, 6 MSMs) of withdraw (real witnesses) + audit_like pairs, witness solve excluded; gnark-algorithm CPU "
               "restatement (oracle/c), not gnark" % (lat_n, lat_t, cores, latency_rate, sus_n, sus_t, sustained_rate))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * lat_t / max(1, args.steps), "higher_is_better": True,
@@ -379,17 +399,20 @@ def main():
     circ_a = ctx.load_circuit(sc_a.ccs, pk_a)
     B = min(circ_w.info["max_batch"], circ_a.info["max_batch"])
     n_sets = 2                                                # alternate inputs between steps
-    dev, host_w, asg_a, out_buf = {}, [], [], {}
+    dev, asg_w, asg_a, out_buf = {}, [], [], {}
     for name, circ in (("w", circ_w), ("a", circ_a)):
         nw = circ.info["nb_wires"]
         dev[name] = []
         for s in range(n_sets):
-            wires = witness_like_wires(B, nw, 1000 * rank + 10 * s + (0 if name == "w" else 5))
+            if name == "w":             # real witnesses: assignments -> full wire vectors with the host solver (untimed)
+                asg, _nv = withdraw_assignments(B, rotate=s + rank)
+                asg_w.append(asg)
+                wires = circ.witness_batch(asg, B, bench_rnd(b"wit%d" % s, B))
+            else:
+                wires = witness_like_wires(B, nw, 1000 * rank + 10 * s + 5)
             t = torch.empty((B * nw, 8), dtype=torch.int32, device="cuda")
             ctx.fr_to_device(wires, t.data_ptr())
             dev[name].append(t)
-            if name == "w":
-                host_w.append(wires)
         out_buf[name] = torch.empty((B, 80), dtype=torch.int32, device="cuda")
     for s in range(n_sets):
         asg_a.append(b"".join(sc_a.assignment_bytes(1000 * rank + 100 * s + i) for i in range(B)))
@@ -415,19 +438,18 @@ def main():
         return sum(step_dev(i, which) for i in range(args.steps))
 
     asg_all = b"".join(asg_a[i % n_sets] for i in range(args.steps))
-    wires_all = b"".join(host_w[i % n_sets] for i in range(args.steps))
-    rnd_w_all = rnd_w * args.steps
+    asg_w_all = b"".join(asg_w[i % n_sets] for i in range(args.steps))
 
     def run_e2e(which="wa"):
-        # ONE call per circuit for all K steps' proofs (what a caller with K*B pending proofs does): the library
-        # pipelines stage A (audit: H2D of the assignments, device witness solver, commitment; withdraw: H2D of the
-        # big-endian wire vectors, conversion, commitment) of one group with the proving of the previous one
+        # ONE g16_prove_batch call per circuit for all K steps' proofs (what a caller with K*B pending proofs does):
+        # the library pipelines stage A (H2D of the assignments, device witness solver incl. the host-evaluated
+        # integer hints of the withdraw circuit, commitment) of one group with the proving of the previous one
         n = 0
         if "a" in which:
             circ_a.prove_batch(asg_all, B * args.steps)
             n += ctx.last_launches()
         if "w" in which:
-            circ_w.prove_wires(wires_all, B * args.steps, rnd_w_all)
+            circ_w.prove_batch(asg_w_all, B * args.steps)
             n += ctx.last_launches()
         return n
 
@@ -466,8 +488,7 @@ def main():
     ctx.profile_enable(False)
     # warm-up with the group size the timed call uses (scratch buffers grow on first use)
     circ_a.prove_batch(asg_all[:min(args.steps, 8) * B * circ_a.n_values * 32], min(args.steps, 8) * B)
-    circ_w.prove_wires(wires_all[:min(args.steps, 8) * B * circ_w.info["nb_wires"] * 32], min(args.steps, 8) * B,
-                       rnd_w_all[:min(args.steps, 8) * B * 96])
+    circ_w.prove_batch(asg_w_all[:min(args.steps, 8) * B * circ_w.n_values * 32], min(args.steps, 8) * B)
     results["e2e"], _ = timed(run_e2e)
     results["e2e_audit"], _ = timed(lambda: run_e2e("a"))
 
@@ -489,7 +510,7 @@ def main():
         acc_launches = prof[0][1] + prof[1][1]
         work = prof[0][2] * IMAD_PER_G1_POINT + prof[1][2] * IMAD_PER_G2_POINT
         achieved = work / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else 0.0
-        h2d = B * (circ_w.info["nb_wires"] * 32 + 96) + B * (circ_a.n_values * 32 + 96 + 32)
+        h2d = B * (circ_w.n_values * 32 + 96 + 32) + B * (circ_a.n_values * 32 + 96 + 32)
         d2h = 2 * B * (320 + 64 + 4)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -497,7 +518,9 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs, IMAD.WIDE)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B, "proofs_per_step_per_gpu": 2 * B,
-                       "audit_witness_solver": circ_a.solver,
+                       "audit_witness_solver": circ_a.solver, "withdraw_witness_solver": circ_w.solver,
+                       "withdraw_witnesses": "real (tests/golden/withdraw_assignments.bin, witness 0 = client/prover-params.toml)",
+                       "audit_like_witnesses": "solved wires follow the SURVEY 8(d) mix (40 % zero, 30 % one, 20 % < 2^8, 10 % uniform)",
                        "l2": "inputs larger than L2 (per-step working set > 400 MB), two input sets alternated",
                        "windows_withdraw": {k: circ_w.info[k] for k in ("window_a", "window_b1", "window_kz", "window_b2")},
                        "windows_audit": {k: circ_a.info[k] for k in ("window_a", "window_b1", "window_kz", "window_b2")}},
