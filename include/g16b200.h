@@ -151,6 +151,15 @@ int g16_prove(g16_circuit* c, const uint8_t* witness_gz, size_t witness_len, con
  * returns the value count in *n_values. */
 int g16_witness_to_assignment(const uint8_t* ccs, size_t ccs_len, const uint8_t* witness_gz, size_t witness_len,
                               uint8_t* assignment_be, size_t* n_values);
+/* Host only: "ACVM-lite" (SURVEY.md 8f-3).  sunspot declares every ACIR witness a circuit reads as a secret input;
+ * when the constraints themselves determine those witnesses (arithmetic gates, limb / bit decompositions, is-zero
+ * gadgets -- the reference's withdraw circuit) this rebuilds the whole assignment from a subset of the input wires,
+ * typically the program's ABI inputs (noir_circuit/src/main.nr:39-53; values as in client/prover-params.toml).
+ * known_wires[i] = wire id (1.. = public inputs, then secret inputs, `.ccs` order), known_values_be = 32 B big-endian
+ * each.  Public inputs may be left out: they are derived like any other wire.  Two-call pattern: assignment_be = NULL
+ * returns the value count.  G16_E_UNSAT when the inputs contradict the constraints or do not determine the rest. */
+int g16_complete_assignment(const uint8_t* ccs, size_t ccs_len, const uint32_t* known_wires, const uint8_t* known_values_be,
+                            size_t n_known, uint8_t* assignment_be, size_t* n_values);
 /* Witness only: full wire vectors (n * nbWires * 32 B big-endian) for n assignments -- the R1CS
  * solve of gnark's Prove, with the BSB22 commitment MSM on the GPU.  rnd as in g16_prove_batch
  * (only the blinder is used). */

@@ -232,6 +232,42 @@ def solve_assignment(ccs: bytes, assignment_be: bytes, nb_wires, blinder_be=None
     return wires.raw, committed.raw[:n_committed * 32]
 
 
+def abi_inputs_to_wires(acir_json: bytes, secret_names, n_public, inputs: dict) -> dict:
+    """Noir ABI inputs (Prover.toml as a dict: hex / decimal strings, ints, lists) -> {gnark wire id: value}.
+
+    ABI parameters are ACIR witnesses 0, 1, ... in declaration order, arrays flattened (`abi.parameters` of
+    target/<name>.json); sunspot maps the public ones to gnark wires 1.. and names the secret ones __witness_<k>
+    (`Secret` list of the .ccs).  Parameters missing from `inputs` are left for g16_complete_assignment to derive."""
+    import json
+    abi = json.loads(acir_json)["abi"]["parameters"]
+    wire_of = {k: 1 + k for k in range(n_public - 1)}
+    for pos, name in enumerate(secret_names):
+        wire_of[int(name.rsplit("_", 1)[1])] = n_public + pos
+    to_int = lambda v: int(v, 0) if isinstance(v, str) else int(v)     # noqa: E731
+    known, k = {}, 0
+    for p in abi:
+        length = p["type"].get("length") if p["type"]["kind"] == "array" else None
+        vals = inputs.get(p["name"])
+        for i in range(length or 1):
+            if vals is not None and k in wire_of:
+                known[wire_of[k]] = to_int(vals[i] if length else vals)
+            k += 1
+    return known
+
+
+def complete_assignment(ccs: bytes, known: dict) -> bytes:
+    """Host only ("ACVM-lite"): {wire id: int value} for a subset of the input wires (the program's ABI inputs) -> the full
+    public + secret assignment, when the circuit's constraints determine the rest (include/g16b200.h)."""
+    lib = _lib.load()
+    ids = (ctypes.c_uint32 * len(known))(*known.keys())
+    vals = b"".join(int(v).to_bytes(32, "big") for v in known.values())
+    n = ctypes.c_size_t(0)
+    check(lib.g16_complete_assignment(ccs, len(ccs), ids, vals, len(known), None, ctypes.byref(n)))
+    buf = ctypes.create_string_buffer(32 * n.value)
+    check(lib.g16_complete_assignment(ccs, len(ccs), ids, vals, len(known), buf, ctypes.byref(n)))
+    return buf.raw
+
+
 def witness_to_assignment(ccs: bytes, witness_gz: bytes) -> bytes:
     """Host only: Noir witness file -> public + secret assignment (32 B big-endian values, `.ccs` order)."""
     lib = _lib.load()

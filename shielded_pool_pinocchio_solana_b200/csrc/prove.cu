@@ -1315,6 +1315,37 @@ int g16_prove(g16_circuit* c, const uint8_t* witness_gz, size_t witness_len, con
     return g16_prove_assignment(c, asg.data(), asg.size() / 32, rnd, proof, proof_len, pw, pw_len);
 }
 
+int g16_complete_assignment(const uint8_t* ccs, size_t ccs_len, const uint32_t* known_wires, const uint8_t* known_values_be,
+                            size_t n_known, uint8_t* assignment_be, size_t* n_values) {
+    if (!ccs || !n_values || (n_known && (!known_wires || !known_values_be))) {
+        set_error("g16_complete_assignment: bad arguments");
+        return G16_E_ARG;
+    }
+    Circuit circ;
+    G16_TRY(parse_ccs(ccs, ccs_len, &circ));
+    const size_t nin = circ.nb_public - 1 + circ.nb_secret;
+    if (!assignment_be) {
+        *n_values = nin;
+        return G16_OK;
+    }
+    if (*n_values < nin) {
+        set_error("g16_complete_assignment: output buffer too small");
+        return G16_E_ARG;
+    }
+    std::vector<std::pair<uint32_t, HFr>> known(n_known);
+    for (size_t i = 0; i < n_known; i++) known[i] = {known_wires[i], HFr::from_be(known_values_be + 32 * i)};
+    std::vector<HFr> asg;
+    std::string err;
+    int rc = complete_assignment(circ, known, &asg, &err);
+    if (rc != G16_OK) {
+        set_error("g16_complete_assignment: " + err);
+        return rc;
+    }
+    for (size_t i = 0; i < nin; i++) asg[i].to_be(assignment_be + 32 * i);
+    *n_values = nin;
+    return G16_OK;
+}
+
 int g16_witness_to_assignment(const uint8_t* ccs, size_t ccs_len, const uint8_t* witness_gz, size_t witness_len,
                               uint8_t* assignment_be, size_t* n_values) {
     if (!ccs || !witness_gz || !n_values) {

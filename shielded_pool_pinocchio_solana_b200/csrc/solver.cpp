@@ -4,6 +4,8 @@
 
 #include <string.h>
 
+#include <algorithm>
+#include <functional>
 #include <map>
 
 #include "common.cuh"
@@ -378,6 +380,459 @@ void solve_provide_challenge(SolveState* st, const HFr& challenge) {
     st->w[st->challenge_wire] = challenge;
     st->known[st->challenge_wire] = 1;
     st->commitments_done++;
+}
+
+}  // namespace g16
+
+// ---------------------------------------------------------------------------------------------------------------------
+// witness completion (see solver.hpp); restated in oracle/py/witness_completion.py, which generated the golden
+// assignments this is tested against (tests/test_withdraw_real.py)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace g16 {
+namespace {
+
+typedef std::vector<std::pair<uint32_t, HFr>> Unk;   // unknown wire -> accumulated coefficient
+
+void unk_add(Unk* u, uint32_t wire, const HFr& coef) {
+    for (auto& e : *u)
+        if (e.first == wire) {
+            e.second = e.second + coef;
+            return;
+        }
+    u->push_back({wire, coef});
+}
+void unk_prune(Unk* u) {
+    Unk o;
+    for (auto& e : *u)
+        if (!e.second.is_zero()) o.push_back(e);
+    u->swap(o);
+}
+const HFr* unk_find(const Unk& u, uint32_t wire) {
+    for (auto& e : u)
+        if (e.first == wire) return &e.second;
+    return nullptr;
+}
+
+struct Completer {
+    const Circuit& c;
+    SolveState st;
+    std::vector<uint8_t> done, queued;
+    std::vector<uint32_t> use_ptr, use_idx;   // CSR: wire -> instructions that READ it
+    std::vector<uint32_t> range_bits;         // 0 = unknown
+    std::vector<uint32_t> queue;
+    size_t qhead = 0;
+    std::string error;
+    size_t violated = 0;
+
+    explicit Completer(const Circuit& circ) : c(circ) {}
+
+    const uint32_t* cd(uint32_t ins) const { return c.calldata.data() + c.start_calldata[ins]; }
+
+    template <class Fn>
+    void for_each_input_wire(uint32_t ins, Fn fn) const {
+        const uint32_t* d = cd(ins);
+        if (c.blueprint[ins] == 1) {
+            const uint32_t nt = d[1] + d[2] + d[3];
+            for (uint32_t k = 0; k < nt; k++)
+                if (d[5 + 2 * k] != CCS_CONST_WIRE) fn(d[5 + 2 * k]);
+        } else {
+            size_t p = 3;
+            for (uint32_t i = 0; i < d[2]; i++) {
+                const uint32_t ln = d[p++];
+                for (uint32_t k = 0; k < ln; k++, p += 2)
+                    if (d[p + 1] != CCS_CONST_WIRE) fn(d[p + 1]);
+            }
+        }
+    }
+
+    void lin(const uint32_t* terms, uint32_t n, HFr* sum, Unk* unk) const {
+        *sum = HFr::zero();
+        unk->clear();
+        for (uint32_t k = 0; k < n; k++) {
+            const uint32_t cid = terms[2 * k], wid = terms[2 * k + 1];
+            const HFr& co = c.coeffs[cid];
+            if (wid == CCS_CONST_WIRE) *sum = *sum + co;
+            else if (!st.known[wid]) unk_add(unk, wid, co);
+            else *sum = *sum + co * st.w[wid];
+        }
+        unk_prune(unk);
+    }
+
+    void set_wire(uint32_t x, const HFr& v) {
+        if (st.known[x]) return;
+        st.w[x] = v;
+        st.known[x] = 1;
+        for (uint32_t k = use_ptr[x]; k < use_ptr[x + 1]; k++) {
+            const uint32_t ins = use_idx[k];
+            if (!done[ins] && !queued[ins]) {
+                queue.push_back(ins);
+                queued[ins] = 1;
+            }
+        }
+    }
+
+    static BigInt canon(const HFr& x) { return BigInt::from_fr(x); }
+
+    // radix rule on  sum coef_i u_i = K
+    bool radix(const Unk& coefs, const HFr& K) {
+        struct Item {
+            size_t e;
+            uint32_t wire;
+        };
+        static const BigInt RM = [] {
+            BigInt m;
+            m.m.assign(HFr::M, HFr::M + 4);
+            return m;
+        }();
+        const BigInt half = RM.shr_mag(1);
+        std::vector<Item> items;
+        int sign = -1;
+        for (auto& e : coefs) {
+            BigInt co = canon(e.second);
+            const bool neg = half < co;
+            BigInt m = neg ? RM - co : co;
+            if (m.is_zero()) return false;
+            const size_t bits = m.bits();
+            if (!(m == BigInt(1).shl(bits - 1))) return false;   // not a power of two
+            if (sign < 0) sign = neg;
+            else if (sign != (int)neg) return false;
+            items.push_back({bits - 1, e.first});
+        }
+        std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.e < b.e; });
+        for (size_t i = 0; i + 1 < items.size(); i++)
+            if (items[i].e == items[i + 1].e) return false;
+        const BigInt Kp = canon(sign ? K.neg() : K);
+        std::vector<BigInt> vals(items.size());
+        BigInt recomposed;
+        for (size_t i = 0; i < items.size(); i++) {
+            const size_t gap = i + 1 < items.size() ? items[i + 1].e - items[i].e : 0;
+            const size_t bw = range_bits[items[i].wire];
+            size_t width = 0;   // 0 = everything above
+            if (bw && gap) width = std::min(bw, gap);
+            else if (bw) width = bw;
+            else width = gap;
+            BigInt v = Kp.shr_mag(items[i].e);
+            if (width) v = v.low_bits(width);
+            vals[i] = v;
+            recomposed = recomposed + v.shl(items[i].e);
+        }
+        if (!(recomposed == Kp)) return false;
+        for (size_t i = 0; i < items.size(); i++) set_wire(items[i].wire, vals[i].to_fr());
+        return true;
+    }
+
+    // one instruction; returns false on a hard error (error set)
+    bool step(uint32_t ins) {
+        const uint32_t* d = cd(ins);
+        if (c.blueprint[ins] != 1) {
+            bool ready = true;
+            for_each_input_wire(ins, [&](uint32_t x) { ready = ready && st.known[x]; });
+            if (!ready) return true;
+            auto kit = c.hint_kinds.find(d[1]);
+            if (kit != c.hint_kinds.end() && kit->second == HINT_COMMIT) {   // the assignment does not depend on it
+                done[ins] = 1;
+                return true;
+            }
+            static const HFr zero_blinder = HFr::zero();
+            bool paused = false;
+            // run_hint marks its outputs known itself; re-announce them so that their readers are queued
+            size_t p = 3;
+            for (uint32_t i = 0; i < d[2]; i++) p += 1 + 2 * (size_t)d[p];
+            const uint32_t o0 = d[p], o1 = d[p + 1];
+            std::vector<uint8_t> was(o1 > o0 ? o1 - o0 : 0);
+            for (uint32_t x = o0; x < o1; x++) was[x - o0] = st.known[x];
+            if (run_hint(c, &st, ins, &zero_blinder, &paused) != G16_OK) {
+                error = st.error;
+                return false;
+            }
+            for (uint32_t x = o0; x < o1; x++)
+                if (!was[x - o0]) {
+                    st.known[x] = 0;
+                    set_wire(x, st.w[x]);
+                }
+            done[ins] = 1;
+            return true;
+        }
+        const uint32_t nl = d[1], nr = d[2], no = d[3];
+        HFr a, b, cc;
+        Unk ua, ub, uc;
+        lin(d + 4, nl, &a, &ua);
+        lin(d + 4 + 2 * nl, nr, &b, &ub);
+        lin(d + 4 + 2 * (nl + nr), no, &cc, &uc);
+        std::vector<uint32_t> unk;
+        for (auto* u : {&ua, &ub, &uc})
+            for (auto& e : *u)
+                if (std::find(unk.begin(), unk.end(), e.first) == unk.end()) unk.push_back(e.first);
+        if (unk.empty()) {
+            done[ins] = 1;
+            if (a * b != cc) {
+                violated++;
+                if (error.empty()) error = "constraint #" + std::to_string(c.constraint_offset[ins]) + " is not satisfied";
+            }
+            return true;
+        }
+        if (unk.size() == 1) {
+            const uint32_t x = unk[0];
+            const HFr *ca = unk_find(ua, x), *cb = unk_find(ub, x), *co = unk_find(uc, x);
+            if (co && !ca && !cb) {
+                set_wire(x, (a * b - cc) * co->inverse());
+            } else if (ca && !cb && !co) {
+                set_wire(x, b.is_zero() ? HFr::zero() : (cc * b.inverse() - a) * ca->inverse());
+            } else if (cb && !ca && !co) {
+                set_wire(x, a.is_zero() ? HFr::zero() : (cc * a.inverse() - b) * cb->inverse());
+            } else if (ca && co && !cb) {
+                const HFr den = *ca * b - *co;
+                if (den.is_zero()) return true;
+                set_wire(x, (cc - a * b) * den.inverse());
+            } else if (cb && co && !ca) {
+                const HFr den = *cb * a - *co;
+                if (den.is_zero()) return true;
+                set_wire(x, (cc - a * b) * den.inverse());
+            } else {
+                return true;   // quadratic in x: left to the linear-system pass or to other rows
+            }
+            done[ins] = 1;
+            return true;
+        }
+        // several unknowns: radix rows
+        if (ua.empty() && ub.empty()) {
+            if (radix(uc, a * b - cc)) done[ins] = 1;
+        } else if (ua.empty() && uc.empty()) {
+            if (!a.is_zero() && radix(ub, cc * a.inverse() - b)) done[ins] = 1;
+        } else if (ub.empty() && uc.empty()) {
+            if (!b.is_zero() && radix(ua, cc * b.inverse() - a)) done[ins] = 1;
+        }
+        return true;
+    }
+
+    bool propagate() {
+        while (qhead < queue.size()) {
+            const uint32_t ins = queue[qhead++];
+            queued[ins] = 0;
+            if (done[ins]) continue;
+            if (!step(ins)) return false;
+        }
+        queue.clear();
+        qhead = 0;
+        return true;
+    }
+
+    // small linear systems over the stalled rows; returns whether any wire was set
+    bool linear_systems(bool fallback) {
+        struct Eq {
+            Unk co;
+            HFr rhs;
+        };
+        std::vector<Eq> eqs;
+        for (uint32_t ins = 0; ins < c.blueprint.size(); ins++) {
+            if (done[ins] || c.blueprint[ins] != 1) continue;
+            const uint32_t* d = cd(ins);
+            const uint32_t nl = d[1], nr = d[2], no = d[3];
+            HFr a, b, cc;
+            Unk ua, ub, uc;
+            lin(d + 4, nl, &a, &ua);
+            lin(d + 4 + 2 * nl, nr, &b, &ub);
+            lin(d + 4 + 2 * (nl + nr), no, &cc, &uc);
+            if (!ua.empty() && !ub.empty()) continue;
+            Eq e;
+            for (auto& t : ua) unk_add(&e.co, t.first, t.second * b);
+            for (auto& t : ub) unk_add(&e.co, t.first, t.second * a);
+            for (auto& t : uc) unk_add(&e.co, t.first, t.second.neg());
+            unk_prune(&e.co);
+            e.rhs = cc - a * b;
+            if (!e.co.empty() && e.co.size() <= 4) eqs.push_back(std::move(e));
+        }
+        if (eqs.empty()) return false;
+        std::map<uint32_t, uint32_t> parent;
+        std::function<uint32_t(uint32_t)> find = [&](uint32_t x) {
+            auto it = parent.find(x);
+            if (it == parent.end()) {
+                parent[x] = x;
+                return x;
+            }
+            if (it->second == x) return x;
+            uint32_t r = find(it->second);
+            parent[x] = r;
+            return r;
+        };
+        for (auto& e : eqs)
+            for (size_t k = 1; k < e.co.size(); k++) parent[find(e.co[k].first)] = find(e.co[0].first);
+        std::map<uint32_t, std::vector<size_t>> comps;
+        for (size_t i = 0; i < eqs.size(); i++) comps[find(eqs[i].co[0].first)].push_back(i);
+        bool progress = false;
+        for (auto& kv : comps) {
+            std::vector<uint32_t> xs;
+            for (size_t i : kv.second)
+                for (auto& t : eqs[i].co)
+                    if (std::find(xs.begin(), xs.end(), t.first) == xs.end()) xs.push_back(t.first);
+            std::sort(xs.begin(), xs.end());
+            if (xs.size() > 40) continue;
+            const size_t nc = xs.size(), nrw = kv.second.size();
+            std::vector<std::vector<HFr>> M(nrw, std::vector<HFr>(nc + 1, HFr::zero()));
+            for (size_t r = 0; r < nrw; r++) {
+                for (auto& t : eqs[kv.second[r]].co) {
+                    const size_t col = std::lower_bound(xs.begin(), xs.end(), t.first) - xs.begin();
+                    M[r][col] = t.second;
+                }
+                M[r][nc] = eqs[kv.second[r]].rhs;
+            }
+            std::vector<size_t> piv;
+            size_t rr = 0;
+            for (size_t col = 0; col < nc && rr < nrw; col++) {
+                size_t p = rr;
+                while (p < nrw && M[p][col].is_zero()) p++;
+                if (p == nrw) continue;
+                std::swap(M[rr], M[p]);
+                const HFr iv = M[rr][col].inverse();
+                for (auto& v : M[rr]) v = v * iv;
+                for (size_t r = 0; r < nrw; r++)
+                    if (r != rr && !M[r][col].is_zero()) {
+                        const HFr f = M[r][col];
+                        for (size_t k = 0; k <= nc; k++) M[r][k] = M[r][k] - f * M[rr][k];
+                    }
+                piv.push_back(col);
+                rr++;
+            }
+            bool inconsistent = false;
+            for (size_t r = rr; r < nrw; r++)
+                if (!M[r][nc].is_zero()) inconsistent = true;
+            if (inconsistent) continue;
+            std::vector<uint8_t> is_piv(nc, 0);
+            for (size_t col : piv) is_piv[col] = 1;
+            bool set_any = false;
+            for (size_t r = 0; r < piv.size(); r++) {
+                bool determined = true;
+                for (size_t col = 0; col < nc; col++)
+                    if (!is_piv[col] && !M[r][col].is_zero()) determined = false;
+                if ((determined || fallback) && !st.known[xs[piv[r]]]) {
+                    set_wire(xs[piv[r]], M[r][nc]);
+                    set_any = true;
+                }
+            }
+            if (fallback) {
+                for (size_t col = 0; col < nc; col++)
+                    if (!is_piv[col] && !st.known[xs[col]]) {
+                        set_wire(xs[col], HFr::zero());
+                        set_any = true;
+                    }
+                if (set_any) return true;   // one component at a time in fallback mode
+            }
+            progress = progress || set_any;
+        }
+        return progress;
+    }
+
+    int run(const std::vector<std::pair<uint32_t, HFr>>& known_in, std::vector<HFr>* assignment) {
+        const uint32_t nw = c.nb_wires();
+        const size_t ninstr = c.blueprint.size();
+        st.w.assign(nw, HFr::zero());
+        st.known.assign(nw, 0);
+        st.w[0] = HFr::one();
+        st.known[0] = 1;
+        done.assign(ninstr, 0);
+        queued.assign(ninstr, 1);
+        // wire -> reader instructions
+        std::vector<uint32_t> cnt(nw + 1, 0);
+        for (uint32_t ins = 0; ins < ninstr; ins++) for_each_input_wire(ins, [&](uint32_t x) { cnt[x + 1]++; });
+        use_ptr.assign(nw + 1, 0);
+        for (uint32_t x = 0; x < nw; x++) use_ptr[x + 1] = use_ptr[x] + cnt[x + 1];
+        use_idx.assign(use_ptr[nw], 0);
+        std::vector<uint32_t> cur(use_ptr.begin(), use_ptr.end() - 1);
+        for (uint32_t ins = 0; ins < ninstr; ins++) for_each_input_wire(ins, [&](uint32_t x) { use_idx[cur[x]++] = ins; });
+        // range information
+        range_bits.assign(nw, 0);
+        auto note = [&](uint32_t wire, uint64_t bits) {
+            if (bits && bits < 400 && (!range_bits[wire] || bits < range_bits[wire])) range_bits[wire] = (uint32_t)bits;
+        };
+        for (uint32_t ins = 0; ins < ninstr; ins++) {
+            const uint32_t* d = cd(ins);
+            if (c.blueprint[ins] != 1) {
+                auto kit = c.hint_kinds.find(d[1]);
+                if (kit == c.hint_kinds.end()) continue;
+                size_t p = 3;
+                std::vector<size_t> starts;
+                for (uint32_t i = 0; i < d[2]; i++) {
+                    starts.push_back(p);
+                    p += 1 + 2 * (size_t)d[p];
+                }
+                const uint32_t nout = d[p + 1] - d[p];
+                auto single_wire = [&](size_t q, uint32_t* wire) {
+                    if (d[q] != 1 || d[q + 2] == CCS_CONST_WIRE || !(c.coeffs[d[q + 1]] == HFr::one())) return false;
+                    *wire = d[q + 2];
+                    return true;
+                };
+                uint32_t wire;
+                if (kit->second == HINT_DECOMPOSE && d[2] == 3 && d[starts[0]] == 1 && d[starts[0] + 2] == CCS_CONST_WIRE &&
+                    single_wire(starts[2], &wire)) {
+                    uint64_t cn[4];
+                    c.coeffs[d[starts[0] + 1]].canonical(cn);
+                    if (!(cn[1] | cn[2] | cn[3])) note(wire, cn[0]);
+                } else if (kit->second == HINT_NBITS && d[2] == 1 && single_wire(starts[0], &wire)) {
+                    note(wire, nout);
+                }
+            } else if (d[1] == 1 && d[2] == 2 && d[3] <= 1 && d[5] != CCS_CONST_WIRE && c.coeffs[d[4]] == HFr::one()) {
+                // b * (1 - b) = 0
+                const uint32_t bw = d[5];
+                bool one_ok = false, minus_ok = false, zero_rhs = true;
+                for (int k = 0; k < 2; k++) {
+                    const uint32_t cid = d[6 + 2 * k], wid = d[7 + 2 * k];
+                    if ((wid == 0 || wid == CCS_CONST_WIRE) && c.coeffs[cid] == HFr::one()) one_ok = true;
+                    if (wid == bw && c.coeffs[cid] == HFr::one().neg()) minus_ok = true;
+                }
+                if (d[3] == 1 && !c.coeffs[d[10]].is_zero()) zero_rhs = false;
+                if (one_ok && minus_ok && zero_rhs) note(bw, 1);
+            }
+        }
+        for (auto& kv : known_in) {
+            if (kv.first >= nw) {
+                error = "known wire out of range";
+                return G16_E_ARG;
+            }
+            st.w[kv.first] = kv.second;
+            st.known[kv.first] = 1;
+        }
+        queue.resize(ninstr);
+        for (uint32_t i = 0; i < ninstr; i++) queue[i] = i;
+        if (!propagate()) return G16_E_HINT;
+        bool fallback = false, fallback_tried = false, progress = true;
+        const uint32_t nin = c.nb_public + c.nb_secret;
+        auto inputs_complete = [&] {
+            for (uint32_t i = 0; i < nin; i++)
+                if (!st.known[i] && use_ptr[i] != use_ptr[i + 1]) return false;
+            return true;
+        };
+        while (progress || !fallback_tried) {
+            if (!progress) {
+                fallback = true;
+                fallback_tried = true;
+            } else {
+                fallback_tried = false;
+                fallback = false;
+            }
+            progress = linear_systems(fallback);
+            if (!propagate()) return G16_E_HINT;
+            if (!progress && fallback_tried) break;
+        }
+        if (violated) return G16_E_UNSAT;
+        if (!inputs_complete()) {
+            uint32_t first = 0;
+            while (first < nin && (st.known[first] || use_ptr[first] == use_ptr[first + 1])) first++;
+            error = "the constraints do not determine input wire " + std::to_string(first);
+            return G16_E_UNSAT;
+        }
+        assignment->assign(st.w.begin() + 1, st.w.begin() + nin);   // unread inputs stay 0
+        return G16_OK;
+    }
+};
+
+}  // namespace
+
+int complete_assignment(const Circuit& c, const std::vector<std::pair<uint32_t, HFr>>& known, std::vector<HFr>* assignment,
+                        std::string* err) {
+    Completer k(c);
+    int rc = k.run(known, assignment);
+    if (rc != G16_OK && err) *err = k.error.empty() ? "witness completion failed" : k.error;
+    return rc;
 }
 
 }  // namespace g16

@@ -8,6 +8,7 @@
 // calls provide_challenge() before run() again.
 #pragma once
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "ccs.hpp"
@@ -40,5 +41,20 @@ int solve_run(const Circuit& c, SolveState* st, const HFr* blinder);
 void solve_provide_challenge(SolveState* st, const HFr& challenge);
 // one hint instruction on its own (the device solver's host-evaluated hints, gpusolver.cuh); G16_OK or a G16_E_* code
 int solve_run_hint(const Circuit& c, SolveState* st, uint32_t instr);
+
+// ---- witness completion ("ACVM-lite") ----------------------------------------------------------
+// sunspot declares every ACIR witness a circuit's constraints read as a secret input, so an assignment normally comes
+// from `nargo execute`.  When the constraints themselves determine those witnesses -- arithmetic gates, limb / bit
+// decompositions, is-zero gadgets: the case of the reference's withdraw circuit -- this rebuilds the assignment from a
+// subset of the inputs (the program's ABI inputs) by data-flow propagation over the R1CS:
+//   1. a row with one unknown wire defines it; a hint runs once its inputs are known;
+//   2. a linear row whose unknowns carry distinct powers of two is a radix decomposition: the known side is split,
+//      widths from the range checks (rangecheck.DecomposeHint, bits.nBits, b * (1 - b) = 0 rows);
+//   3. what stalls after that is solved as small linear systems (rows linear in their unknowns, per connected
+//      component, Gaussian elimination over Fr); a variable that stays free is set to 0.
+// `known`: (wire id, value) pairs.  On success `assignment` holds nb_public-1 + nb_secret values (Montgomery).
+// Returns G16_OK, G16_E_UNSAT (a fully known row does not hold, or inputs stay undetermined) or G16_E_HINT.
+int complete_assignment(const Circuit& c, const std::vector<std::pair<uint32_t, HFr>>& known, std::vector<HFr>* assignment,
+                        std::string* err);
 
 }  // namespace g16

@@ -99,3 +99,46 @@ def test_a_wrong_private_input_is_rejected(circuit, fixtures):
     pk, _vk, _ = G.setup(circuit, b"withdraw-real", fast=True)
     with pytest.raises(G.Unsatisfied):
         G.solve(circuit, asg, pk=pk, blinder=1)
+
+
+def test_product_completion_equals_the_fixtures(circuit, fixtures):
+    """g16_complete_assignment (C++, host only): from the private ABI inputs alone, byte-identical to every committed
+    assignment (which the Python restatement generated)."""
+    import shielded_pool_pinocchio_solana_b200 as g16
+    meta, blobs = fixtures
+    raw = open(os.path.join(GOLD, "shielded_pool_verifier.ccs"), "rb").read()
+    wmap = gen.wire_of_abi(circuit)
+    for n, blob in enumerate(blobs):
+        abi = {name: int(v, 16) for name, v in meta["witnesses"][n].items()}
+        known = {wmap[k]: abi[name] for k, name in enumerate(gen.ABI) if name not in gen.DERIVED}
+        assert g16.complete_assignment(raw, known) == blob, "witness %d" % n
+
+
+def test_prover_toml_front_door_and_rejections(circuit, fixtures):
+    """Prover.toml + the program's ABI (target/<name>.json) -> assignment: what `nargo execute` + sunspot's witness
+    ingest do for this circuit (noir_circuit/prove_linux.sh:62-83), without an ACVM."""
+    import tomllib
+    import shielded_pool_pinocchio_solana_b200 as g16
+    meta, blobs = fixtures
+    raw = open(os.path.join(GOLD, "shielded_pool_verifier.ccs"), "rb").read()
+    abi_json = open(os.path.join(GOLD, "shielded_pool_verifier.abi.json"), "rb").read()
+    toml = tomllib.load(open(os.path.join(GOLD, "prover-params.toml"), "rb"))
+    names = circuit.body["Secret"]
+    # every input given (as a caller holding Prover.toml would): completion also CHECKS the public inputs
+    known = g16.abi_inputs_to_wires(abi_json, names, circuit.nb_public, toml)
+    assert len(known) == 26
+    assert g16.complete_assignment(raw, known) == blobs[0]
+    # private inputs only: the public ones are derived
+    private = {k: v for k, v in toml.items() if k not in ("root", "nullifier", "wa_commitment", "owner_x", "owner_y")}
+    assert g16.complete_assignment(raw, g16.abi_inputs_to_wires(abi_json, names, circuit.nb_public, private)) == blobs[0]
+    # a wrong Merkle root contradicts the constraints (propagation runs backwards from it into a failing row or a
+    # failing range-check lookup, whichever comes first)
+    bad = dict(toml, root="0x%064x" % (int(toml["root"], 16) ^ 1))
+    with pytest.raises(g16.G16Error) as e:
+        g16.complete_assignment(raw, g16.abi_inputs_to_wires(abi_json, names, circuit.nb_public, bad))
+    assert e.value.code in (3, 5)
+    # without the secret key nothing determines the key pair: rejected as well
+    short = {k: v for k, v in private.items() if k != "secret_key"}
+    with pytest.raises(g16.G16Error) as e:
+        g16.complete_assignment(raw, g16.abi_inputs_to_wires(abi_json, names, circuit.nb_public, short))
+    assert e.value.code in (3, 5)
