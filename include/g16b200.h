@@ -160,6 +160,12 @@ int g16_witness_to_assignment(const uint8_t* ccs, size_t ccs_len, const uint8_t*
  * returns the value count.  G16_E_UNSAT when the inputs contradict the constraints or do not determine the rest. */
 int g16_complete_assignment(const uint8_t* ccs, size_t ccs_len, const uint32_t* known_wires, const uint8_t* known_values_be,
                             size_t n_known, uint8_t* assignment_be, size_t* n_values);
+/* Host only: `nargo execute` for such circuits (noir_circuit/prove_linux.sh:62, client/proof.helper.ts:55).  Prover.toml
+ * (scalars as "0x.." / decimal, arrays) + the compiled program's JSON (only `abi.parameters` is read) + the .ccs ->
+ * the witness file `sunspot prove` / g16_prove read (gzip of a bincode WitnessStack).  Inputs the TOML leaves out
+ * (e.g. the public ones) are derived; inputs it gives are checked.  Two-call pattern on witness_gz / *witness_len. */
+int g16_execute(const uint8_t* ccs, size_t ccs_len, const char* acir_json, size_t acir_len, const char* prover_toml,
+                size_t toml_len, uint8_t* witness_gz, size_t* witness_len);
 /* Witness only: full wire vectors (n * nbWires * 32 B big-endian) for n assignments -- the R1CS
  * solve of gnark's Prove, with the BSB22 commitment MSM on the GPU.  rnd as in g16_prove_batch
  * (only the blinder is used). */

@@ -72,6 +72,8 @@ PROTOTYPES = {
                                              ctypes.c_char_p, ctypes.c_char_p]),
     "g16_complete_assignment": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), ctypes.c_char_p,
                                                ctypes.c_size_t, ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t)]),
+    "g16_execute": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p,
+                                   ctypes.c_size_t, ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t)]),
     "g16_witness_to_assignment": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
                                                  ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t)]),
     "g16_set_deferred_join": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

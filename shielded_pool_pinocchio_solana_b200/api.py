@@ -268,6 +268,17 @@ def complete_assignment(ccs: bytes, known: dict) -> bytes:
     return buf.raw
 
 
+def execute(ccs: bytes, acir_json: bytes, prover_toml: bytes) -> bytes:
+    """Host only: Prover.toml + program ABI + .ccs -> witness file (gzip), for circuits whose constraints determine their
+    witnesses (`nargo execute` stand-in; include/g16b200.h g16_execute)."""
+    lib = _lib.load()
+    n = ctypes.c_size_t(0)
+    check(lib.g16_execute(ccs, len(ccs), acir_json, len(acir_json), prover_toml, len(prover_toml), None, ctypes.byref(n)))
+    buf = ctypes.create_string_buffer(n.value)
+    check(lib.g16_execute(ccs, len(ccs), acir_json, len(acir_json), prover_toml, len(prover_toml), buf, ctypes.byref(n)))
+    return buf.raw[:n.value]
+
+
 def witness_to_assignment(ccs: bytes, witness_gz: bytes) -> bytes:
     """Host only: Noir witness file -> public + secret assignment (32 B big-endian values, `.ccs` order)."""
     lib = _lib.load()

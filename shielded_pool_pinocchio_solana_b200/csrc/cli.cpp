@@ -4,6 +4,10 @@
 //        (/root/reference/client/proof.helper.ts:64, noir_circuit/prove_linux.sh:83); writes
 //        <dir-of-ccs>/<name>.proof and <name>.pw, the files proof.helper.ts:68-69 and
 //        client/generate-proof-hex.ts:18-27 read back.
+//        <witness.gz> may be a Prover.toml instead (name ending in .toml): the witness is then rebuilt from it
+//        (g16_execute), for circuits whose constraints determine their witnesses -- the withdraw circuit
+//   g16prove execute <acir.json> <Prover.toml> <ccs> <witness.gz-out>   that step alone (`nargo execute`, prove_linux.sh:62;
+//        host only, no GPU needed)
 //   g16prove setup <ccs>                                    same argv as `sunspot setup` (prove_linux.sh:78):
 //        writes <name>.pk and <name>.vk next to the .ccs; fresh OS entropy (aborts if it cannot be read)
 //   g16prove setup <ccs> <pk-out> <vk-out> [seed]           explicit outputs / reproducible seed (tests)
@@ -40,7 +44,8 @@ static int die(const char* what) {
 
 int main(int argc, char** argv) {
     if (argc < 2) {
-        fprintf(stderr, "usage: g16prove prove <acir.json> <witness.gz> <ccs> <pk>\n"
+        fprintf(stderr, "usage: g16prove prove <acir.json> <witness.gz | Prover.toml> <ccs> <pk>\n"
+                        "       g16prove execute <acir.json> <Prover.toml> <ccs> <witness.gz-out>\n"
                         "       g16prove setup <ccs> [<pk-out> <vk-out> [seed]]\n"
                         "       g16prove verify <vk> <proof> <pw>\n");
         return 2;
@@ -61,15 +66,50 @@ int main(int argc, char** argv) {
         printf("proof accepted\n");
         return 0;
     }
+    auto execute = [](const char* acir_path, const char* toml_path, const std::vector<uint8_t>& ccs, std::vector<uint8_t>* gz) {
+        std::vector<uint8_t> acir, toml;
+        if (!slurp(acir_path, &acir) || !slurp(toml_path, &toml)) {
+            fprintf(stderr, "g16prove: cannot read %s / %s\n", acir_path, toml_path);
+            return false;
+        }
+        size_t n = 0;
+        if (g16_execute(ccs.data(), ccs.size(), (const char*)acir.data(), acir.size(), (const char*)toml.data(), toml.size(), nullptr, &n) != G16_OK) {
+            die("execute");
+            return false;
+        }
+        gz->resize(n);
+        if (g16_execute(ccs.data(), ccs.size(), (const char*)acir.data(), acir.size(), (const char*)toml.data(), toml.size(), gz->data(), &n) != G16_OK) {
+            die("execute");
+            return false;
+        }
+        gz->resize(n);
+        return true;
+    };
+    if (cmd == "execute" && argc == 6) {   // host only
+        std::vector<uint8_t> ccs, gz;
+        if (!slurp(argv[4], &ccs)) {
+            fprintf(stderr, "g16prove: cannot read %s\n", argv[4]);
+            return 1;
+        }
+        if (!execute(argv[2], argv[3], ccs, &gz)) return 1;
+        if (!spill(argv[5], gz.data(), gz.size())) {
+            fprintf(stderr, "g16prove: cannot write %s\n", argv[5]);
+            return 1;
+        }
+        return 0;
+    }
     int dev = getenv("G16_DEVICE") ? atoi(getenv("G16_DEVICE")) : 0;
     g16_ctx* ctx = nullptr;
     if (g16_init(&dev, 1, &ctx) != G16_OK) return die("init");
     if (cmd == "prove" && argc == 6) {
         std::vector<uint8_t> acir, gz, ccs, pk;
-        if (!slurp(argv[3], &gz) || !slurp(argv[4], &ccs) || !slurp(argv[5], &pk)) {
+        const std::string wpath = argv[3];
+        const bool from_toml = wpath.size() > 5 && wpath.compare(wpath.size() - 5, 5, ".toml") == 0;
+        if ((!from_toml && !slurp(argv[3], &gz)) || !slurp(argv[4], &ccs) || !slurp(argv[5], &pk)) {
             fprintf(stderr, "g16prove: cannot read input files\n");
             return 1;
         }
+        if (from_toml && !execute(argv[2], argv[3], ccs, &gz)) return 1;
         slurp(argv[2], &acir);  // optional: the .ccs name lists carry the witness mapping
         g16_circuit* c = nullptr;
         if (g16_circuit_load(ctx, ccs.data(), ccs.size(), pk.data(), pk.size(), nullptr, &c) != G16_OK) return die("load");

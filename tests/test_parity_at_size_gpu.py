@@ -250,4 +250,27 @@ def test_withdraw_real_witnesses_prove_bit_exact_and_verify(ctx):
     body = struct.pack("<QIQ", 1, 0, len(acir)) + b"".join(struct.pack("<IQ", k, 32) + v for k, v in sorted(acir.items()))
     p0, w0 = circ.prove(gzip.compress(body), rnd[:96])
     assert p0 == proofs[0] and w0 == pws[0]
+    # ... and straight from Prover.toml: g16_execute rebuilds the witness file `nargo execute` would write
+    toml = open(os.path.join(GOLD, "prover-params.toml"), "rb").read()
+    abi_json = open(os.path.join(GOLD, "shielded_pool_verifier.abi.json"), "rb").read()
+    p1, w1 = circ.prove(g16.execute(raw, abi_json, toml), rnd[:96])
+    assert p1 == proofs[0] and w1 == pws[0]
     circ.free()
+    # the CLI with sunspot's argv, Prover.toml in place of the witness file (prove_linux.sh:62-87 without nargo)
+    import shutil
+    import subprocess
+    import tempfile
+    exe = os.path.join(os.path.dirname(g16.LIB_PATH), "g16prove")
+    with tempfile.TemporaryDirectory() as d:
+        for name in ("shielded_pool_verifier.abi.json", "prover-params.toml", "shielded_pool_verifier.ccs"):
+            shutil.copy(os.path.join(GOLD, name), d)
+        open(os.path.join(d, "shielded_pool_verifier.pk"), "wb").write(pk)
+        open(os.path.join(d, "shielded_pool_verifier.vk"), "wb").write(vk)
+        j = lambda n: os.path.join(d, n)     # noqa: E731
+        r = subprocess.run([exe, "prove", j("shielded_pool_verifier.abi.json"), j("prover-params.toml"),
+                            j("shielded_pool_verifier.ccs"), j("shielded_pool_verifier.pk")], capture_output=True)
+        assert r.returncode == 0, r.stderr
+        assert open(j("shielded_pool_verifier.pw"), "rb").read() == pws[0]
+        r = subprocess.run([exe, "verify", j("shielded_pool_verifier.vk"), j("shielded_pool_verifier.proof"),
+                            j("shielded_pool_verifier.pw")], capture_output=True)
+        assert r.returncode == 0 and b"accepted" in r.stdout

@@ -142,3 +142,29 @@ def test_prover_toml_front_door_and_rejections(circuit, fixtures):
     with pytest.raises(g16.G16Error) as e:
         g16.complete_assignment(raw, g16.abi_inputs_to_wires(abi_json, names, circuit.nb_public, short))
     assert e.value.code in (3, 5)
+
+
+def test_execute_c_abi_and_cli(fixtures, tmp_path):
+    """g16_execute / `g16prove execute`: Prover.toml + ABI + .ccs -> the witness file (`nargo execute`,
+    prove_linux.sh:62), host only; reading it back through the witness ingest gives the committed assignment."""
+    import subprocess
+    import shielded_pool_pinocchio_solana_b200 as g16
+    meta, blobs = fixtures
+    raw = open(os.path.join(GOLD, "shielded_pool_verifier.ccs"), "rb").read()
+    abi_json = open(os.path.join(GOLD, "shielded_pool_verifier.abi.json"), "rb").read()
+    toml = open(os.path.join(GOLD, "prover-params.toml"), "rb").read()
+    gz = g16.execute(raw, abi_json, toml)
+    assert gz[:2] == b"\x1f\x8b" and g16.witness_to_assignment(raw, gz) == blobs[0]
+    exe = os.path.join(ROOT, "shielded_pool_pinocchio_solana_b200", "g16prove")
+    out = tmp_path / "w.gz"
+    r = subprocess.run([exe, "execute", os.path.join(GOLD, "shielded_pool_verifier.abi.json"),
+                        os.path.join(GOLD, "prover-params.toml"), os.path.join(GOLD, "shielded_pool_verifier.ccs"), str(out)],
+                       capture_output=True)
+    assert r.returncode == 0, r.stderr
+    assert g16.witness_to_assignment(raw, out.read_bytes()) == blobs[0]
+    # a Prover.toml whose secret key does not match its public key is refused with a non-zero exit
+    bad = tmp_path / "bad.toml"
+    bad.write_bytes(toml.replace(b"43f5147fe5a665df", b"43f5147fe5a665de"))
+    r = subprocess.run([exe, "execute", os.path.join(GOLD, "shielded_pool_verifier.abi.json"), str(bad),
+                        os.path.join(GOLD, "shielded_pool_verifier.ccs"), str(out)], capture_output=True)
+    assert r.returncode != 0 and b"execute" in r.stderr
