@@ -43,6 +43,13 @@ function circuitFor(config: CircuitConfig): g16.Circuit {
 
 function runNargo(config: CircuitConfig, inputs: ShieldedPoolInputs): Buffer {
   fs.writeFileSync(path.join(config.circuitDir, "Prover.toml"), proverToml(inputs as unknown as Record<string, unknown>));
+  if (process.env.G16_NO_NARGO) {
+    // withdraw circuit: its constraints determine every intermediate witness, so the library rebuilds the witness file
+    // from Prover.toml itself (g16_execute) -- no Noir toolchain on the proving host
+    const base = path.join(config.circuitDir, "target", config.circuitName);
+    return g16.execute(fs.readFileSync(`${base}.ccs`), fs.readFileSync(`${base}.json`),
+                       fs.readFileSync(path.join(config.circuitDir, "Prover.toml")));
+  }
   execSync("nargo execute", { cwd: config.circuitDir });
   return fs.readFileSync(path.join(config.circuitDir, "target", `${config.circuitName}.gz`));
 }

@@ -275,12 +275,33 @@ napi_value Setup(napi_env env, napi_callback_info info) {
   return obj;
 }
 
+// execute(ccs: Buffer, programJson: Buffer, proverToml: Buffer) -> Buffer (the witness file `nargo execute` writes);
+// host only.  For circuits whose constraints determine their witnesses (the withdraw circuit): include/g16b200.h.
+napi_value Execute(napi_env env, napi_callback_info info) {
+  size_t argc = 3;
+  napi_value argv[3];
+  napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+  const uint8_t *ccs, *acir, *toml;
+  size_t nccs, nacir, ntoml;
+  if (argc < 3 || !buffer_arg(env, argv[0], &ccs, &nccs) || !buffer_arg(env, argv[1], &acir, &nacir) ||
+      !buffer_arg(env, argv[2], &toml, &ntoml))
+    return throw_error(env, "execute(ccs: Buffer, programJson: Buffer, proverToml: Buffer)");
+  size_t n = 0;
+  if (g16_execute(ccs, nccs, (const char*)acir, nacir, (const char*)toml, ntoml, nullptr, &n) != G16_OK)
+    return throw_error(env, g16_last_error());
+  std::vector<uint8_t> gz(n);
+  if (g16_execute(ccs, nccs, (const char*)acir, nacir, (const char*)toml, ntoml, gz.data(), &n) != G16_OK)
+    return throw_error(env, g16_last_error());
+  return make_buffer(env, gz.data(), n);
+}
+
 }  // namespace
 
 NAPI_MODULE_INIT() {
   struct { const char* name; napi_callback fn; } fns[] = {
       {"loadCircuit", LoadCircuit}, {"proveSync", ProveSync}, {"prove", Prove},
       {"proveBatch", ProveBatch},   {"verify", Verify},       {"setup", Setup},
+      {"execute", Execute},
   };
   for (auto& f : fns) {
     napi_value v;

@@ -8,4 +8,6 @@ export function prove(circuit: Circuit, witnessGz: Buffer): Promise<ProofFiles>;
 export function proveBatch(circuit: Circuit, assignments: Buffer, n: number):
   Promise<{ proofs: Buffer; publicWitnesses: Buffer; pwStride: number }>;
 export function verify(vk: Buffer, proof: Buffer, publicWitness: Buffer): boolean;
+/** `nargo execute` stand-in for circuits whose constraints determine their witnesses: Prover.toml -> witness file. */
+export function execute(ccs: Buffer, programJson: Buffer, proverToml: Buffer): Buffer;
 export function setup(ccs: Buffer, seed: Buffer, device?: number): { pk: Buffer; vk: Buffer };
