@@ -16,6 +16,8 @@
 
 #include <string.h>
 
+#include <algorithm>
+
 namespace g16 {
 
 namespace {
@@ -348,6 +350,7 @@ void GpuSolverPlan::release() {
     d_host_wires = nullptr;
     host_hints.clear();
     host_wires.clear();
+    host_inputs.clear();
     d_lvl_off = d_lvl_instr = d_instr_cd = d_calldata = nullptr;
     d_info = nullptr;
     d_coeff_invs = nullptr;
@@ -434,6 +437,18 @@ int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not
                         return G16_OK;
                     }
                     host_hints.push_back(ins);
+                    {
+                        size_t q2 = 3;
+                        for (uint32_t i = 0; i < nin; i++) {
+                            const uint32_t ln = cd[q2++];
+                            for (uint32_t t = 0; t < ln; t++, q2 += 2) {
+                                const uint32_t wid = cd[q2 + 1];
+                                if (wid != CCS_CONST_WIRE && wid != 0 && wid < c.nb_public + c.nb_secret &&
+                                    std::find(host_inputs.begin(), host_inputs.end(), wid) == host_inputs.end())
+                                    host_inputs.push_back(wid);
+                            }
+                        }
+                    }
                     for (uint32_t wv = o0; wv < o1 && wv < nw; wv++) {
                         host_wires.push_back(wv);
                         host_known[wv] = 1;

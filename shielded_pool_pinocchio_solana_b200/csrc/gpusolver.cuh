@@ -26,6 +26,7 @@ struct GpuSolverPlan {
     // the device solve and their outputs are scattered into the wire vectors like extra inputs.
     std::vector<uint32_t> host_hints;   // instruction ids, in dependency order
     std::vector<uint32_t> host_wires;   // their output wires, concatenated
+    std::vector<uint32_t> host_inputs;  // the circuit INPUT wires those hints read (only these are converted on the host)
     uint32_t* d_host_wires = nullptr;
 
     // Compiles the plan; leaves valid == false (and says why) when the circuit needs the host solver.

@@ -201,7 +201,8 @@ struct BigInt {
         mod.m.assign(HFr::M, HFr::M + 4);
         BigInt q, r, am = *this;
         am.neg = false;
-        divmod_mag(am, mod, &q, &r);
+        if (cmp_mag(am, mod) < 0) r = am;   // the usual case (limbs, carries): no division
+        else divmod_mag(am, mod, &q, &r);
         uint64_t c[4] = {0, 0, 0, 0};
         for (size_t i = 0; i < r.m.size() && i < 4; i++) c[i] = r.m[i];
         HFr x = HFr{{c[0], c[1], c[2], c[3]}}.to_mont();

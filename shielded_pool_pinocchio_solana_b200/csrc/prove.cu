@@ -1032,11 +1032,14 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
         const size_t workers = std::min<size_t>(default_threads(), B);
         parallel_for(workers, [&](size_t t) {
             SolveState stt;
-            std::vector<HFr> asg(nin);
+            std::vector<HFr> asg(nin, HFr::zero());
+            solve_begin(circ, asg.data(), &stt);
             for (size_t b = t; b < B; b += workers) {
+                // only the inputs these hints read are converted; their outputs are forgotten between proofs
                 const uint8_t* src = assignments_be + b * nin * 32;
-                for (size_t i = 0; i < nin; i++) asg[i] = HFr::from_be(src + 32 * i);
-                solve_begin(circ, asg.data(), &stt);
+                for (uint32_t wv : c->plan.host_inputs) stt.w[wv] = HFr::from_be(src + 32 * (size_t)(wv - 1));
+                for (uint32_t wv : c->plan.host_wires) stt.known[wv] = 0;
+                stt.error.clear();
                 stt.tolerate = tolerate;
                 for (uint32_t ins : c->plan.host_hints)
                     if ((rcs[b] = solve_run_hint(circ, &stt, ins)) != G16_OK) {

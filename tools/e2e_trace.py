@@ -34,6 +34,14 @@ t0 = time.time(); circ_w.prove_wires(wires_all, B * chunks, rnd_all); t1 = time.
 print("prove_wires: %.1f ms per 64-proof chunk" % ((t1 - t0) * 1e3 / chunks))
 t0 = time.time(); circ_w.prove_wires(wires, B, rnd); t1 = time.time()
 print("prove_wires, one chunk alone: %.1f ms" % ((t1 - t0) * 1e3))
+asg_w, _nv = bench.withdraw_assignments(B * chunks)
+circ_w.prove_batch(asg_w, B * chunks)
+print("=== traced withdraw prove_batch (real witnesses)", file=sys.stderr, flush=True)
+t0 = time.time(); circ_w.prove_batch(asg_w, B * chunks); t1 = time.time()
+print("withdraw prove_batch (real witnesses, device solver): %.1f ms per 64-proof chunk" % ((t1 - t0) * 1e3 / chunks))
+wires_real = circ_w.witness_batch(asg_w[:B * _nv * 32], B)
+t0 = time.time(); circ_w.prove_wires(wires_real * chunks, B * chunks, rnd_all); t1 = time.time()
+print("withdraw prove_wires (real wires): %.1f ms per 64-proof chunk" % ((t1 - t0) * 1e3 / chunks))
 os.environ["G16_SOLVE_OVERLAP"] = "0"
 print("=== traced prove_batch, no overlap", file=sys.stderr, flush=True)
 t0 = time.time(); circ_a.prove_batch(asg_all, B * chunks); t1 = time.time()
