@@ -1058,7 +1058,21 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
     }
     const bool commit = c->plan.commit_level != (uint32_t)-1;
     const uint32_t split = commit ? c->plan.commit_level + 1 : c->plan.nlevels;
-    if ((rc = c->plan.run(c->d_coeffs, c->unit_ids, W, c->wstride, c->nw, B, 0, split, d_err, st)) != G16_OK) return failm(rc, get_error());
+    // All proofs of the group are solved at once.  Solving them `sub` at a time (G16_SOLVE_SUB; fewer resident solver
+    // CTAs taking registers from the accumulate kernels next to them) was measured: the latency-bound solver then
+    // runs four times as long beside the prover and becomes the bottleneck of the pipeline (19.1 -> 22.2 ms per audit
+    // chunk, 29.5 -> 43.2 per withdraw chunk at sub = 64).
+    static const size_t sub_env = getenv("G16_SOLVE_SUB") ? (size_t)atol(getenv("G16_SOLVE_SUB")) : 0;
+    const size_t sub = sub_env ? sub_env : B;
+    auto run_levels = [&](uint32_t lv0, uint32_t lv1) {
+        for (size_t off = 0; off < B; off += sub) {
+            int r = c->plan.run(c->d_coeffs, c->unit_ids, W + off * c->wstride, c->wstride, c->nw, std::min(sub, B - off), lv0, lv1,
+                                d_err + off, st);
+            if (r != G16_OK) return r;
+        }
+        return (int)G16_OK;
+    };
+    if ((rc = run_levels(0, split)) != G16_OK) return failm(rc, get_error());
     sl.commits.assign(B, G1Affine::inf());
     if (commit) {
         rc = c->g1_aux.run(c->bCommit, W, c->wstride, c->d_map_commit, 1, B, (G1Affine*)sl.d_commit_out.ptr, st);
@@ -1076,8 +1090,7 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
         trace("solve_gpu: challenges hashed");
         G16_STAGE_CUDA(cudaMemcpyAsync(sl.d_chal.ptr, h_chal, sizeof(Fr) * B, cudaMemcpyHostToDevice, st));
         if ((rc = c->plan.set_wire(W, c->wstride, c->plan.commit_wire, (const Fr*)sl.d_chal.ptr, B, st)) != G16_OK) return failm(rc, get_error());
-        if ((rc = c->plan.run(c->d_coeffs, c->unit_ids, W, c->wstride, c->nw, B, split, c->plan.nlevels, d_err, st)) != G16_OK)
-            return failm(rc, get_error());
+        if ((rc = run_levels(split, c->plan.nlevels)) != G16_OK) return failm(rc, get_error());
     }
     G16_STAGE_CUDA(cudaMemcpyAsync(h_err, d_err, 4 * B, cudaMemcpyDeviceToHost, st));
     G16_STAGE_CUDA(cudaEventRecord(sl.ready, st));
