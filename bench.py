@@ -33,6 +33,8 @@ import argparse
 import hashlib
 import json
 import os
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA is initialised: see _lib.py
 import subprocess
 import sys
 import threading

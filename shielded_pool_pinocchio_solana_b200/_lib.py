@@ -7,6 +7,11 @@ raises, loudly.
 import ctypes
 import os
 
+# One circuit handle drives ~20 CUDA streams; with the default of 8 hardware connections they alias and the witness
+# stage of the next group queues behind kernels of the current one (csrc/capi.cu g16_init).  The variable is read when
+# the CUDA context is created, so it is set here, before torch or the library touch the device.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libg16b200.so")
 

@@ -197,6 +197,11 @@ int g16_init(const int* device_ids, int n_devices, g16_ctx** out) {
         set_error("g16_init: exactly one device per context (one process per GPU)");
         return G16_E_ARG;
     }
+    // A circuit handle drives ~20 streams (one per MSM, the side streams, the witness stage).  With the default of 8
+    // hardware connections they alias: the witness stage of group k+1 then waits behind whole kernel sequences of
+    // group k that merely share its queue (measured: 38 ms for a 1 ms copy).  Read when the CUDA context is created,
+    // so it only takes effect if this is the first CUDA user of the process (the Python package sets it at import).
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {

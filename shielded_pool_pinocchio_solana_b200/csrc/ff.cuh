@@ -339,9 +339,9 @@ struct alignas(16) Field {
     // shifts, additions and subtractions on the ALU pipe only (~15 K simple instructions, no
     // multiplier), with x1 started at R^2 so that the result is already in Montgomery form:
     //   invariants  x1 * X = u * R^2,  x2 * X = v * R^2  (mod p)   =>  u = 1: x1 = R^2 / X = (a^-1) R.
-    // This is the inversion behind the batched-affine bucket additions (msm.cuh, kernel B) and the
-    // affine normalisations; it is ~4x shorter in latency than the Fermat ladder.
-    FF_HD Field inverse() const {
+    // Data-dependent loops: fine for one value on the host, divergent when the lanes of a warp invert different
+    // values.  Kept as a second cross-check of inverse().
+    FF_HD Field inverse_euclid() const {
         if (is_zero()) return *this;
         uint32_t u[8], w[8], t[8];
 #pragma unroll
@@ -379,7 +379,149 @@ struct alignas(16) Field {
         return is_one(u) ? x1 : x2;
     }
 
+
+    // Inverse (0 -> 0) with a fixed instruction sequence: the binary GCD on 64-bit approximations of Pornin
+    // ("Optimized binary GCD for modular inversion", 2020).  17 rounds; each runs 30 halving/subtract steps on
+    // (low 31 bits | top 33 bits) of a and b while tracking the 2x2 update matrix (f0 g0; f1 g1), |.| <= 2^30, then
+    // applies it to the full values:  (a, b) <- (f0 a + g0 b, f1 a + g1 b) / 2^30  (exact) and
+    // (u, v) <- (f0 u + g0 v, f1 u + g1 v) / 2^30 mod p  (one Montgomery word step).  Invariants a = u X / R^2,
+    // b = v X / R^2 with u0 = R^2, v0 = 0; after 510 >= 2*254 - 1 steps b = gcd = 1 and v = R^2 / X = (a^-1) R.
+    // No branch depends on the data, so the 32 lanes of a warp can invert 32 different values in lockstep (the
+    // witness solver's division rows); ~3x fewer instructions than the shift/subtract loop of inverse_euclid().
+    FF_HD Field inverse() const {
+        uint32_t a[8], b[8], m[8];
+        Field U = r2(), V = zero();
+        modulus(m);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            a[i] = v[i];
+            b[i] = m[i];
+        }
+        for (int round = 0; round < 17; round++) {
+            // ---- approximations: n = bit length of max(a, b); keep bits [0, 31) and [n - 33, n)
+            uint32_t hi_a = 0, mi_a = 0, lo_a = 0, hi_b = 0, mi_b = 0, lo_b = 0, top = 0;
+            int j = 0;
+#pragma unroll
+            for (int i = 7; i >= 2; i--) {
+                const bool here = top == 0 && (a[i] | b[i]) != 0;
+                if (here) {
+                    top = a[i] | b[i];
+                    j = i;
+                    hi_a = a[i], mi_a = a[i - 1], lo_a = a[i - 2];
+                    hi_b = b[i], mi_b = b[i - 1], lo_b = b[i - 2];
+                }
+            }
+            uint64_t xa, xb;
+            if (j == 0) {   // n <= 64: exact
+                xa = ((uint64_t)a[1] << 32) | a[0];
+                xb = ((uint64_t)b[1] << 32) | b[0];
+            } else {
+#ifdef __CUDA_ARCH__
+                const int s = __clz((int)top);
+#else
+                const int s = __builtin_clz(top);   // top != 0
+#endif
+                const uint64_t ta = ((((uint64_t)hi_a << 32) | mi_a) << s) | (s ? (uint64_t)(lo_a >> (32 - s)) : 0);
+                const uint64_t tb = ((((uint64_t)hi_b << 32) | mi_b) << s) | (s ? (uint64_t)(lo_b >> (32 - s)) : 0);
+                xa = ((ta >> 31) << 31) | (a[0] & 0x7fffffffu);
+                xb = ((tb >> 31) << 31) | (b[0] & 0x7fffffffu);
+            }
+            // ---- 30 steps on the approximations
+            int32_t f0 = 1, g0 = 0, f1 = 0, g1 = 1;
+            for (int i = 0; i < 30; i++) {
+                const bool odd = xa & 1u;
+                const bool swap = odd && xa < xb;
+                const uint64_t ta = swap ? xb : xa, tb = swap ? xa : xb;
+                const int32_t tf0 = swap ? f1 : f0, tf1 = swap ? f0 : f1, tg0 = swap ? g1 : g0, tg1 = swap ? g0 : g1;
+                xa = (ta - (odd ? tb : 0)) >> 1;
+                xb = tb;
+                f0 = tf0 - (odd ? tf1 : 0);
+                g0 = tg0 - (odd ? tg1 : 0);
+                f1 = tf1 * 2;
+                g1 = tg1 * 2;
+            }
+            // ---- (a, b) <- (f0 a + g0 b, f1 a + g1 b) / 2^30, made non-negative (flip the matrix row with it)
+            uint32_t na[9], nb[9];
+            ff_lincomb9(na, a, f0, b, g0);
+            ff_lincomb9(nb, a, f1, b, g1);
+            if (na[8] & 0x80000000u) {
+                ff_neg9(na);
+                f0 = -f0, g0 = -g0;
+            }
+            if (nb[8] & 0x80000000u) {
+                ff_neg9(nb);
+                f1 = -f1, g1 = -g1;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                a[i] = (na[i] >> 30) | (na[i + 1] << 2);
+                b[i] = (nb[i] >> 30) | (nb[i + 1] << 2);
+            }
+            // ---- (u, v) <- (f0 u + g0 v, f1 u + g1 v) / 2^30 mod p
+            const Field nu = mont_step30(U, f0, V, g0), nv = mont_step30(U, f1, V, g1);
+            U = nu;
+            V = nv;
+        }
+        return V;
+    }
+
    private:
+    // out (9 limbs, two's complement) = f x + g y,  |f| + |g| <= 2^30 ... 2^31: every partial sum fits an int64
+    FF_HD static void ff_lincomb9(uint32_t* out, const uint32_t* x, int32_t f, const uint32_t* y, int32_t g) {
+        int64_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            acc += (int64_t)x[i] * f + (int64_t)y[i] * g;
+            out[i] = (uint32_t)acc;
+            acc >>= 32;
+        }
+        out[8] = (uint32_t)acc;
+    }
+    FF_HD static void ff_neg9(uint32_t* t) {
+        uint32_t c = 1;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            const uint32_t x = ~t[i] + c;
+            c = (c && x == 0) ? 1u : 0u;
+            t[i] = x;
+        }
+    }
+    // (f x + g y) / 2^30 mod p for x, y in [0, p), |f| + |g| <= 2^30
+    FF_HD static Field mont_step30(const Field& x, int32_t f, const Field& y, int32_t g) {
+        uint32_t t[9], m[8];
+        modulus(m);
+        ff_lincomb9(t, x.v, f, y.v, g);   // |t| < 2^30 p
+        // t += 2^30 p: non-negative, same residue
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            const uint32_t lo = i == 0 ? 0u : (m[i - 1] >> 2), hi = i < 8 ? (m[i] << 30) : 0u;
+            c += (uint64_t)t[i] + (lo | hi);
+            t[i] = (uint32_t)c;
+            c >>= 32;
+        }
+        // t += k p with k = -t / p mod 2^30: the low 30 bits clear
+        const uint32_t k = (t[0] * PM::INV) & 0x3fffffffu;
+        c = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            c += (uint64_t)t[i] + (uint64_t)m[i] * k;
+            t[i] = (uint32_t)c;
+            c >>= 32;
+        }
+        t[8] += (uint32_t)c;
+        Field r;   // t / 2^30 < 3p
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = (t[i] >> 30) | (t[i + 1] << 2);
+        uint32_t d[8];
+        for (int it = 0; it < 2; it++) {
+            const bool below = ff_sub8(d, r.v, m) != 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) r.v[i] = below ? r.v[i] : d[i];
+        }
+        return r;
+    }
+
     // lo += a_even*bi ; y (old lo-aligned, limb0 cleared) shifts into hi alignment += a_odd*bi
     FF_HD static void round_mul(uint32_t* lo, uint32_t* y, const Field& a, uint32_t bi) {
         ff_mad4_shift(y, lo[0], a.v[1], a.v[3], a.v[5], a.v[7], bi);

@@ -281,6 +281,80 @@ k_solve_tpi(const uint32_t* __restrict__ lvl_off, const uint4* __restrict__ rec,
     }
 }
 
+// ---- thread-per-proof variant for runs of thin levels -----------------------------------------------------
+// The tail of the reference withdraw circuit is one dependent chain: ~650 levels of 1-6 short rows, every second
+// or third of them a division (the affine point additions of the in-circuit scalar multiplication).  A CTA per
+// proof would sit on an SM for the whole chain with one lane working, and (measured) takes the registers of one
+// bucket-accumulation CTA of the concurrently running MSMs with it.  Here a THREAD owns a proof and walks the rows
+// of [lvl_begin, lvl_end) in plan order (no barrier: program order is the dependency order), so a 256-proof group
+// is 8 warps; the plan is the same for every lane and Fr::inverse() has no data-dependent branch, so the 32 proofs
+// of a warp stay in lockstep.  Wire loads are one 32-byte sector per lane.
+constexpr int NARROW_THREADS = 32;
+__global__ void __launch_bounds__(NARROW_THREADS)
+k_solve_narrow(const uint32_t* __restrict__ lvl_off, const uint4* __restrict__ rec, const uint32_t* __restrict__ calldata,
+               const Fr* __restrict__ coeffs, const Fr* __restrict__ coeff_invs, Fr* wires, size_t wstride,
+               size_t blinder_slot, uint32_t lvl_begin, uint32_t lvl_end, int unit_ids, uint32_t* err, uint32_t B) {
+    const uint32_t b = blockIdx.x * NARROW_THREADS + threadIdx.x;
+    if (b >= B) return;
+    Fr* w = wires + (size_t)b * wstride;
+    uint32_t* e = err + b;
+    const uint32_t k_end = lvl_off[lvl_end];
+    for (uint32_t k = lvl_off[lvl_begin]; k < k_end; k++) {
+        const uint4 inf = rec[2 * k], shp = rec[2 * k + 1];
+        const uint32_t* cd = calldata + shp.x;
+        if (inf.x >= 16) {
+            run_hint(inf.x - 16, cd, w, coeffs, unit_ids, w[blinder_slot], e);
+            continue;
+        }
+        const uint32_t nl = shp.y, nlr = shp.y + shp.z, nt = nlr + shp.w;
+        const uint32_t skip = inf.x == 0 ? NO_WIRE : inf.y;
+        const uint32_t* terms = cd + 4;
+        Fr L = Fr::zero(), Rr = Fr::zero(), O = Fr::zero();
+        for (uint32_t i0 = 0; i0 < nt; i0 += 4) {
+            uint32_t cid[4], wid[4];
+            Fr x[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t i = i0 + j;
+                cid[j] = i < nt ? terms[2 * i] : 0u;
+                wid[j] = i < nt ? terms[2 * i + 1] : skip;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                x[j] = Fr::zero();
+                if (i0 + j < nt && wid[j] != skip && wid[j] != CCS_CONST_WIRE) x[j] = w[wid[j]];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t i = i0 + j;
+                if (i >= nt || wid[j] == skip) continue;
+                Fr v;
+                if (wid[j] == CCS_CONST_WIRE) v = coeffs[cid[j]];
+                else if (unit_ids && cid[j] == 1) v = x[j];
+                else if (unit_ids && cid[j] == 3) v = x[j].neg();
+                else if (unit_ids && cid[j] == 0) continue;
+                else v = coeffs[cid[j]] * x[j];
+                if (i < nl) L = L + v;
+                else if (i < nlr) Rr = Rr + v;
+                else O = O + v;
+            }
+        }
+        if (inf.x == 0) {
+            if (L * Rr != O) atomicMin(e, inf.w + 1);
+        } else if (inf.x == 1) {
+            const Fr v = L * Rr - O;
+            w[inf.y] = (unit_ids && inf.z == 1) ? v : ((unit_ids && inf.z == 3) ? v.neg() : v * coeff_invs[inf.z]);
+        } else {
+            // division rows: zero divisor -> gnark leaves the wire at 0 and only checks the row (0 == O)
+            const Fr den = inf.x == 2 ? Rr : L, oth = inf.x == 2 ? L : Rr;
+            if (den.is_zero()) {
+                if (!O.is_zero()) atomicMin(e, inf.w + 1);
+                w[inf.y] = Fr::zero();
+            } else w[inf.y] = (O * den.inverse() - oth) * coeff_invs[inf.z];
+        }
+    }
+}
+
 // assignment (big-endian canonical) -> wires[b][1..nin] (Montgomery), wire 0 = 1, X_* slots from rnd
 __global__ void __launch_bounds__(256)
 k_assign(const uint8_t* __restrict__ asg_be, const uint8_t* __restrict__ rnd_be, uint32_t nin, Fr* __restrict__ wires,
@@ -351,6 +425,7 @@ void GpuSolverPlan::release() {
     host_hints.clear();
     host_wires.clear();
     host_inputs.clear();
+    segments.clear();
     d_lvl_off = d_lvl_instr = d_instr_cd = d_calldata = nullptr;
     d_info = nullptr;
     d_coeff_invs = nullptr;
@@ -506,6 +581,42 @@ int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not
             return G16_OK;
         }
     nlevels = (uint32_t)c.levels.size();
+    // runs of thin levels (few short rows each) go to the thread-per-proof kernel
+    {
+        static const long thin_rows = getenv("G16_SOLVER_THIN_ROWS") ? atol(getenv("G16_SOLVER_THIN_ROWS")) : 8;
+        static const long thin_terms_env = getenv("G16_SOLVER_THIN_TERMS") ? atol(getenv("G16_SOLVER_THIN_TERMS")) : 256;
+        const uint32_t thin_terms = (uint32_t)thin_terms_env, min_run = 16;
+        std::vector<uint8_t> thin(nlevels, 0);
+        for (uint32_t lv = 0; lv < nlevels; lv++) {
+            const uint32_t s0 = lvl_off[lv], t0 = lvl_off[lv + 1];
+            if ((long)(t0 - s0) > thin_rows) continue;
+            uint32_t terms = 0;
+            bool hint = false;
+            for (uint32_t k = s0; k < t0; k++) {
+                const uint32_t ins = lvl_instr[k];
+                const uint32_t* cd = c.calldata.data() + c.start_calldata[ins];
+                if (c.blueprint[ins] == 1) terms += cd[1] + cd[2] + cd[3];
+                else hint = true;
+            }
+            thin[lv] = !hint && terms <= thin_terms;
+        }
+        segments.clear();
+        for (uint32_t lv = 0; lv < nlevels;) {
+            uint32_t e = lv;
+            while (e < nlevels && thin[e] == thin[lv]) e++;
+            const bool narrow = thin[lv] && e - lv >= min_run;
+            if (!segments.empty() && segments.back().narrow == narrow) segments.back().end = e;
+            else segments.push_back({lv, e, narrow});
+            lv = e;
+        }
+        // a short thin run between two wide ones stays wide: merge neighbours of equal kind
+        std::vector<Segment> merged;
+        for (const Segment& sg : segments) {
+            if (!merged.empty() && merged.back().narrow == sg.narrow) merged.back().end = sg.end;
+            else merged.push_back(sg);
+        }
+        segments.swap(merged);
+    }
     std::vector<uint4> rec(2 * lvl_instr.size());
     for (size_t k = 0; k < lvl_instr.size(); k++) {
         const uint32_t ins = lvl_instr[k];
@@ -543,9 +654,25 @@ int GpuSolverPlan::run(const Fr* d_coeffs, int unit_ids, Fr* d_wires, size_t wst
         k_solve_levels<<<(unsigned)B, SOLVE_THREADS, 0, st>>>(d_lvl_off, d_lvl_instr, d_info, d_instr_cd, d_calldata, d_coeffs,
                                                               d_coeff_invs, d_wires, wstride, nw + X_BLINDER, lvl_begin,
                                                               lvl_end, unit_ids, d_err);
-    else
-        k_solve_tpi<<<(unsigned)B, SOLVE_TT, 0, st>>>(d_lvl_off, d_rec, d_calldata, d_coeffs, d_coeff_invs, d_wires, wstride,
-                                                           nw + X_BLINDER, lvl_begin, lvl_end, unit_ids, d_err);
+    else {
+        static const bool no_narrow = getenv("G16_SOLVER_NARROW") && atoi(getenv("G16_SOLVER_NARROW")) == 0;
+        static const bool trace_sync = getenv("G16_TRACE_SYNC") && atoi(getenv("G16_TRACE_SYNC")) != 0;
+        for (const Segment& sg : segments) {
+            const uint32_t lo = std::max(sg.begin, lvl_begin), hi = std::min(sg.end, lvl_end);
+            if (lo >= hi) continue;
+            if (trace_sync) {
+                cudaStreamSynchronize(st);
+                trace(sg.narrow ? "  sync: before narrow segment" : "  sync: before wide segment", (long)lo);
+            }
+            if (sg.narrow && !no_narrow)
+                k_solve_narrow<<<cdiv(B, NARROW_THREADS), NARROW_THREADS, 0, st>>>(d_lvl_off, d_rec, d_calldata, d_coeffs,
+                                                                                  d_coeff_invs, d_wires, wstride, nw + X_BLINDER,
+                                                                                  lo, hi, unit_ids, d_err, (uint32_t)B);
+            else
+                k_solve_tpi<<<(unsigned)B, SOLVE_TT, 0, st>>>(d_lvl_off, d_rec, d_calldata, d_coeffs, d_coeff_invs, d_wires,
+                                                              wstride, nw + X_BLINDER, lo, hi, unit_ids, d_err);
+        }
+    }
     G16_CUDA(cudaGetLastError());
     return G16_OK;
 }

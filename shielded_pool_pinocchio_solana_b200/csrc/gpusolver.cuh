@@ -28,6 +28,12 @@ struct GpuSolverPlan {
     std::vector<uint32_t> host_wires;   // their output wires, concatenated
     std::vector<uint32_t> host_inputs;  // the circuit INPUT wires those hints read (only these are converted on the host)
     uint32_t* d_host_wires = nullptr;
+    // level ranges by kernel: wide levels run a CTA per proof (k_solve_tpi), runs of thin levels a thread per proof
+    struct Segment {
+        uint32_t begin, end;
+        bool narrow;
+    };
+    std::vector<Segment> segments;
 
     // Compiles the plan; leaves valid == false (and says why) when the circuit needs the host solver.
     int build(const Circuit& c, cudaStream_t st, std::string* why_not);

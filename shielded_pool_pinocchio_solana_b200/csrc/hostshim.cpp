@@ -21,7 +21,7 @@ static void st(uint32_t* p, const T& t) {
 
 extern "C" {
 
-// op: 0 mul, 1 add, 2 sub, 3 neg(a), 4 inverse(a), 5 to_mont(a), 6 from_mont(a), 7 sqr(a), 8 inverse_fermat(a), 9 halve(a)
+// op: 0 mul, 1 add, 2 sub, 3 neg(a), 4 inverse(a), 5 to_mont(a), 6 from_mont(a), 7 sqr(a), 8 inverse_fermat(a), 9 halve(a), 10 inverse_euclid(a)
 void shim_fp_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     Fp x = ld<Fp>(a), y = ld<Fp>(b), r;
     switch (op) {
@@ -34,6 +34,7 @@ void shim_fp_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
         case 6: r = x.from_mont(); break;
         case 8: r = x.inverse_fermat(); break;
         case 9: r = x.halve(); break;
+        case 10: r = x.inverse_euclid(); break;
         default: r = x.sqr(); break;
     }
     st(out, r);
@@ -50,6 +51,7 @@ void shim_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
         case 6: r = x.from_mont(); break;
         case 8: r = x.inverse_fermat(); break;
         case 9: r = x.halve(); break;
+        case 10: r = x.inverse_euclid(); break;
         default: r = x.sqr(); break;
     }
     st(out, r);

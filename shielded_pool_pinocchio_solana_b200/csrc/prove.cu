@@ -638,7 +638,8 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
     c->max_batch = max_batch;
     // the solver is latency-bound (one CTA per proof walks ~10^3 levels): give it 4 proving batches at a
     // time so its latency hides behind the proving of the previous group
-    const size_t solve_batch = max_batch >= 8 ? 4 * max_batch : max_batch;
+    const size_t group_chunks = getenv("G16_SOLVE_GROUP") ? std::max(1l, atol(getenv("G16_SOLVE_GROUP"))) : 4;
+    const size_t solve_batch = max_batch >= 8 ? group_chunks * max_batch : max_batch;
     c->solve_batch = solve_batch;
     // ---- bases -------------------------------------------------------------------------------
     auto win = [&](size_t npts) { return msm_pick_window(npts, max_batch); };
@@ -1015,13 +1016,22 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
             v.to_be(h_rnd + 32 * k);
         }
     trace("solve_gpu: staged");
+    // G16_TRACE_SYNC=1: wait for the stream after every step so that the trace shows where the device time goes
+    static const bool trace_sync = getenv("G16_TRACE_SYNC") && atoi(getenv("G16_TRACE_SYNC")) != 0;
+    auto tsync = [&](const char* tag) {
+        if (!trace_sync) return;
+        cudaStreamSynchronize(st);
+        trace(tag);
+    };
     Fr* W = (Fr*)sl.d_wires.ptr;
     uint32_t* d_err = (uint32_t*)sl.d_err.ptr;
     G16_STAGE_CUDA(cudaMemcpyAsync(sl.d_asg_be.ptr, h_asg, 32 * nin * B, cudaMemcpyHostToDevice, st));
     G16_STAGE_CUDA(cudaMemcpyAsync(sl.d_rnd_be.ptr, h_rnd, 96 * B, cudaMemcpyHostToDevice, st));
     G16_STAGE_CUDA(cudaMemsetAsync(d_err, 0xff, 4 * B, st));
+    tsync("  sync: inputs copied");
     int rc = c->plan.assign((const uint8_t*)sl.d_asg_be.ptr, (const uint8_t*)sl.d_rnd_be.ptr, (uint32_t)nin, W, c->wstride, c->nw, B, st);
     if (rc != G16_OK) return failm(rc, get_error());
+    tsync("  sync: k_assign");
     if (!c->plan.host_hints.empty()) {
         // integer hints that hang off the inputs (withdraw circuit: the Grumpkin scalar split and its emulated product
         // check): evaluated on the host per proof, scattered into the device wire vectors before level 0
@@ -1030,6 +1040,7 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
         std::vector<int> rcs(B, G16_OK);
         std::vector<std::string> errs(B);
         const size_t workers = std::min<size_t>(default_threads(), B);
+        trace("solve_gpu: inputs enqueued");
         parallel_for(workers, [&](size_t t) {
             SolveState stt;
             std::vector<HFr> asg(nin, HFr::zero());
@@ -1051,9 +1062,11 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
         });
         for (size_t b = 0; b < B; b++)
             if (rcs[b] != G16_OK && !tolerate) return failm(rcs[b], "proof " + std::to_string(first_index + b) + ": " + errs[b]);
+        trace("solve_gpu: host hints evaluated");
         if (sl.d_pre.ensure(sizeof(Fr) * npre * B) != G16_OK) return failm(G16_E_CUDA, get_error());
         G16_STAGE_CUDA(cudaMemcpyAsync(sl.d_pre.ptr, pre.data(), sizeof(Fr) * npre * B, cudaMemcpyHostToDevice, st));
         G16_STAGE_CUDA(cudaStreamSynchronize(st));   // `pre` is pageable and dies with this scope
+        trace("solve_gpu: hint outputs on the device");
         if ((rc = c->plan.scatter_host_wires(W, c->wstride, (const Fr*)sl.d_pre.ptr, B, st)) != G16_OK) return failm(rc, get_error());
     }
     const bool commit = c->plan.commit_level != (uint32_t)-1;
@@ -1073,11 +1086,13 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
         return (int)G16_OK;
     };
     if ((rc = run_levels(0, split)) != G16_OK) return failm(rc, get_error());
+    tsync("  sync: levels before the commitment");
     sl.commits.assign(B, G1Affine::inf());
     if (commit) {
         rc = c->g1_aux.run(c->bCommit, W, c->wstride, c->d_map_commit, 1, B, (G1Affine*)sl.d_commit_out.ptr, st);
         if (rc != G16_OK) return failm(rc, get_error());
         k_fp_from_mont<<<cdiv(B * 2, 256), 256, 0, st>>>((Fp*)sl.d_commit_out.ptr, B * 2);
+        tsync("  sync: commitment MSM");
         trace("solve_gpu: phase1 enqueued");
         G16_STAGE_CUDA(cudaMemcpyAsync(sl.commits.data(), sl.d_commit_out.ptr, sizeof(G1Affine) * B, cudaMemcpyDeviceToHost, st));
         G16_STAGE_CUDA(cudaStreamSynchronize(st));

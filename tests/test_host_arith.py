@@ -49,16 +49,19 @@ def test_field_ops_match_bigint():
 
 
 def test_binary_gcd_inverse_equals_fermat_and_bigint():
-    """inverse() (binary extended Euclid on the Montgomery representative) = inverse_fermat() = the
-    big-integer inverse: for X = aR the result is a^-1 R = R^2 / X."""
+    """inverse() (fixed-sequence binary GCD on 64-bit approximations) = inverse_euclid() (shift/subtract extended
+    Euclid) = inverse_fermat() = the big-integer inverse: for X = aR the result is a^-1 R = R^2 / X."""
     rng = random.Random(12)
     for fn, m in ((SHIM.shim_fp_op, B.P), (SHIM.shim_fr_op, B.R)):
-        xs = [e % m for e in EDGE] + [m - 1, m - 2, (m - 1) // 2] + [rng.randrange(1, m) for _ in range(300)]
+        xs = [e % m for e in EDGE] + [m - 1, m - 2, (m - 1) // 2] + [rng.randrange(1, m) for _ in range(2000)]
         xs += [1 << k for k in range(0, 254, 7)] + [(m - (1 << k)) % m for k in range(0, 254, 11)]
         for a in xs:
             want = 0 if a == 0 else MONT * MONT * B.inv(a, m) % m
             assert fop(fn, 4, a) == want
+        for a in xs[:400]:
+            want = 0 if a == 0 else MONT * MONT * B.inv(a, m) % m
             assert fop(fn, 8, a) == want
+            assert fop(fn, 10, a) == want
 
 
 def test_fp2_ops():
