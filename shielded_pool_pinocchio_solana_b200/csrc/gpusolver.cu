@@ -74,7 +74,7 @@ __device__ void run_hint(uint32_t kind, const uint32_t* __restrict__ cd, Fr* __r
     switch (kind) {
         case HINT_NBITS: {
             Fr c = input(0).from_mont();
-            for (uint32_t k = 0; k < nout; k++) w[o0 + k] = fr_from_u32(canon_bits(c, k, 1));
+            for (uint32_t k = 0; k < nout; k++) w[o0 + k] = canon_bits(c, k, 1) ? Fr::one() : Fr::zero();
             break;
         }
         case HINT_INVZERO:
@@ -101,9 +101,26 @@ __device__ void run_hint(uint32_t kind, const uint32_t* __restrict__ cd, Fr* __r
             uint32_t table_q = q;
             for (uint32_t i = 0; i < size; i++) q += 1 + 2 * cd[q];
             Fr one = Fr::one();
+            // range-check tables are the values 0..size-1 in order: a query v then counts for row v (no other row
+            // holds v, so this is the first match the scan would find); any other table takes the scan
+            bool identity = q - table_q == 3 * size;
+            {
+                Fr cur = Fr::zero();
+                for (uint32_t j = 0; j < size && identity; j++) {
+                    identity = cd[table_q + 3 * j] == 1 && lin_eval(cd + table_q + 3 * j + 1, 1, w, coeffs, NO_WIRE, unit_ids) == cur;
+                    cur = cur + one;
+                }
+            }
             for (uint32_t qi = 2 + size; qi < nin; qi++) {
                 Fr val = lin_eval(cd + q + 1, cd[q], w, coeffs, NO_WIRE, unit_ids);
                 q += 1 + 2 * cd[q];
+                if (identity) {
+                    const Fr c = val.from_mont();
+                    if (c.v[0] < size && !(c.v[1] | c.v[2] | c.v[3] | c.v[4] | c.v[5] | c.v[6] | c.v[7])) {
+                        w[o0 + c.v[0]] = w[o0 + c.v[0]] + one;
+                        continue;
+                    }
+                }
                 uint32_t t = table_q;
                 bool found = false;
                 for (uint32_t j = 0; j < size; j++) {
