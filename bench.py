@@ -489,8 +489,9 @@ def main():
     results["prof"] = ctx.profile_read()
     ctx.profile_enable(False)
     # warm-up with the group size the timed call uses (scratch buffers grow on first use)
-    circ_a.prove_batch(asg_all[:min(args.steps, 8) * B * circ_a.n_values * 32], min(args.steps, 8) * B)
-    circ_w.prove_batch(asg_w_all[:min(args.steps, 8) * B * circ_w.n_values * 32], min(args.steps, 8) * B)
+    nwarm = min(args.steps, 12)          # 12 chunks = the 4-chunk first group + one full 8-chunk group
+    circ_a.prove_batch(asg_all[:nwarm * B * circ_a.n_values * 32], nwarm * B)
+    circ_w.prove_batch(asg_w_all[:nwarm * B * circ_w.n_values * 32], nwarm * B)
     results["e2e"], _ = timed(run_e2e)
     results["e2e_audit"], _ = timed(lambda: run_e2e("a"))
 

@@ -298,6 +298,82 @@ k_solve_tpi(const uint32_t* __restrict__ lvl_off, const uint4* __restrict__ rec,
     }
 }
 
+// ---- two-phase variant (default for wide levels) ------------------------------------------------------------
+// Beside the prover the solve is not bound by its latency but by the instructions it issues (the step is issue-bound
+// and k_solve_tpi executes ~5 M warp instructions per proof: its four lanes per row all run the multiply and the three
+// side additions whenever one lane of the warp needs them).  Here the plan is compiled further on the host:
+//   * every term whose coefficient is not 0 / +1 / -1 becomes a PRODUCT of its (sub-)level: phase A computes them with
+//     one thread per product -- full warps of multiplies and nothing else -- into shared memory;
+//   * a row keeps, per side, a list of (code, ref) operands: a product slot, +wire, -wire or a constant; zero terms and
+//     the term of the wire the row defines are dropped at compile time.  Phase B: one thread per row adds the operands
+//     of L, R and O and finishes the row.
+// Levels with more products than the shared-memory buffer are split into sub-levels (rows of one level are
+// independent).  Two barriers per sub-level.
+constexpr int SOLVE2_THREADS = 128;
+constexpr uint32_t SOLVE2_PRODUCTS = 1024;   // 32 KB of shared memory
+enum : uint32_t { OPD_PRODUCT = 0, OPD_PLUS = 1, OPD_CONST = 2, OPD_MINUS = 3 };
+
+__device__ __forceinline__ Fr side_sum(const uint2* __restrict__ ops, uint32_t n, const Fr* w, const Fr* __restrict__ coeffs,
+                                       const Fr* prod) {
+    Fr acc = Fr::zero();
+#pragma unroll 2
+    for (uint32_t i = 0; i < n; i++) {
+        const uint2 d = ops[i];
+        const Fr* src = d.x == OPD_PRODUCT ? prod + d.y : (d.x == OPD_CONST ? coeffs + d.y : w + d.y);
+        const Fr v = *src;
+        acc = acc + (d.x == OPD_MINUS ? v.neg() : v);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(SOLVE2_THREADS, 4)
+k_solve_2p(const uint32_t* __restrict__ sub_off, const uint32_t* __restrict__ prod_off, const uint2* __restrict__ prods,
+           const uint4* __restrict__ rec, const uint2* __restrict__ ops, const uint32_t* __restrict__ calldata,
+           const Fr* __restrict__ coeffs, const Fr* __restrict__ coeff_invs, Fr* wires, size_t wstride, size_t blinder_slot,
+           uint32_t sub_begin, uint32_t sub_end, int unit_ids, uint32_t* err) {
+    __shared__ Fr prod[SOLVE2_PRODUCTS];
+    const uint32_t b = blockIdx.x;
+    Fr* w = wires + (size_t)b * wstride;
+    uint32_t* e = err + b;
+    for (uint32_t sl = sub_begin; sl < sub_end; sl++) {
+        const uint32_t p0 = prod_off[sl], p1 = prod_off[sl + 1];
+        for (uint32_t t = p0 + threadIdx.x; t < p1; t += SOLVE2_THREADS) {
+            const uint2 d = prods[t];
+            prod[t - p0] = coeffs[d.x] * w[d.y];
+        }
+        if (p1 > p0) __syncthreads();
+        const uint32_t s = sub_off[sl], t1 = sub_off[sl + 1];
+        for (uint32_t k = s + threadIdx.x; k < t1; k += SOLVE2_THREADS) {
+            const uint4 inf = rec[2 * k], shp = rec[2 * k + 1];
+            if (inf.x >= 16) {
+                run_hint(inf.x - 16, calldata + shp.x, w, coeffs, unit_ids, w[blinder_slot], e);
+                continue;
+            }
+            const uint2* o = ops + shp.x;
+            const Fr L = side_sum(o, shp.y, w, coeffs, prod);
+            const Fr Rr = side_sum(o + shp.y, shp.z, w, coeffs, prod);
+            const Fr O = side_sum(o + shp.y + shp.z, shp.w, w, coeffs, prod);
+            if (inf.x == 0) {
+                if (L * Rr != O) atomicMin(e, inf.w + 1);           // constraint row (1-based)
+            } else if (inf.x == 1) {
+                const Fr v = L * Rr - O;
+                w[inf.y] = inf.z == 1 ? v : (inf.z == 3 ? v.neg() : v * coeff_invs[inf.z >> 2]);
+            } else {
+                // division rows: zero divisor -> gnark leaves the wire at 0 and only checks the row (0 == O)
+                const Fr den = inf.x == 2 ? Rr : L, oth = inf.x == 2 ? L : Rr;
+                if (den.is_zero()) {
+                    if (!O.is_zero()) atomicMin(e, inf.w + 1);
+                    w[inf.y] = Fr::zero();
+                } else {
+                    const Fr v = O * den.inverse() - oth;
+                    w[inf.y] = inf.z == 1 ? v : (inf.z == 3 ? v.neg() : v * coeff_invs[inf.z >> 2]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- thread-per-proof variant for runs of thin levels -----------------------------------------------------
 // The tail of the reference withdraw circuit is one dependent chain: ~650 levels of 1-6 short rows, every second
 // or third of them a division (the affine point additions of the in-circuit scalar multiplication).  A CTA per
@@ -437,6 +513,11 @@ void GpuSolverPlan::release() {
     cudaFree(d_coeff_invs);
     cudaFree(d_rec);
     d_rec = nullptr;
+    cudaFree(d_sub_off); cudaFree(d_prod_off); cudaFree(d_prods); cudaFree(d_ops); cudaFree(d_rec2);
+    d_sub_off = d_prod_off = nullptr;
+    d_prods = d_ops = nullptr;
+    d_rec2 = nullptr;
+    lvl_to_sub.clear();
     cudaFree(d_host_wires);
     d_host_wires = nullptr;
     host_hints.clear();
@@ -634,6 +715,82 @@ int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not
         }
         segments.swap(merged);
     }
+    // ---- two-phase plan (k_solve_2p): products per sub-level, operand lists per row
+    {
+        const HFr one = HFr::one(), minus_one = HFr::one().neg();
+        std::vector<uint32_t> sub_off(1, 0), prod_off(1, 0);
+        std::vector<uint2> prods, ops;
+        std::vector<uint4> rec2;
+        lvl_to_sub.assign(nlevels + 1, 0);
+        for (uint32_t lv = 0; lv < nlevels; lv++) {
+            lvl_to_sub[lv] = (uint32_t)sub_off.size() - 1;
+            uint32_t in_sub = 0;   // products of the open sub-level
+            auto close_sub = [&]() {
+                sub_off.push_back((uint32_t)(rec2.size() / 2));
+                prod_off.push_back((uint32_t)prods.size());
+                in_sub = 0;
+            };
+            for (uint32_t k = lvl_off[lv]; k < lvl_off[lv + 1]; k++) {
+                const uint32_t ins = lvl_instr[k];
+                const uint32_t* cd = c.calldata.data() + c.start_calldata[ins];
+                if (c.blueprint[ins] != 1) {
+                    rec2.push_back(info[ins]);
+                    rec2.push_back(make_uint4(instr_cd[ins], 0, 0, 0));
+                    continue;
+                }
+                const uint32_t cnt[3] = {cd[1], cd[2], cd[3]};
+                const uint32_t unk = info[ins].x == 0 ? NO_WIRE : info[ins].y;
+                uint32_t row_products = 0;
+                for (uint32_t t = 0; t < cnt[0] + cnt[1] + cnt[2]; t++) {
+                    const uint32_t cid = cd[4 + 2 * t], wid = cd[5 + 2 * t];
+                    if (wid != unk && wid != CCS_CONST_WIRE && !c.coeffs[cid].is_zero() && !(c.coeffs[cid] == one) && !(c.coeffs[cid] == minus_one))
+                        row_products++;
+                }
+                if (row_products > SOLVE2_PRODUCTS) {
+                    *why_not = "a row with more than " + std::to_string(SOLVE2_PRODUCTS) + " non-unit terms";
+                    return G16_OK;
+                }
+                if (in_sub + row_products > SOLVE2_PRODUCTS) close_sub();
+                uint32_t kept[3] = {0, 0, 0};
+                const uint32_t first_op = (uint32_t)ops.size();
+                size_t p = 4;
+                for (int side = 0; side < 3; side++)
+                    for (uint32_t t = 0; t < cnt[side]; t++, p += 2) {
+                        const uint32_t cid = cd[p], wid = cd[p + 1];
+                        if (wid == unk) continue;                       // the wire this row defines
+                        const HFr& cf = c.coeffs[cid];
+                        if (cf.is_zero()) continue;
+                        if (wid == CCS_CONST_WIRE) ops.push_back(make_uint2(OPD_CONST, cid));
+                        else if (cf == one) ops.push_back(make_uint2(OPD_PLUS, wid));
+                        else if (cf == minus_one) ops.push_back(make_uint2(OPD_MINUS, wid));
+                        else {
+                            ops.push_back(make_uint2(OPD_PRODUCT, in_sub++));
+                            prods.push_back(make_uint2(cid, wid));
+                        }
+                        kept[side]++;
+                    }
+                // coefficient of the defined wire: 1 -> +1, 3 -> -1 (by VALUE), else 4*cid (never 1 or 3)
+                uint4 inf = info[ins];
+                if (unk != NO_WIRE) {
+                    const HFr& uc = c.coeffs[inf.z];
+                    inf.z = uc == one ? 1u : (uc == minus_one ? 3u : inf.z << 2);
+                }
+                rec2.push_back(inf);
+                rec2.push_back(make_uint4(first_op, kept[0], kept[1], kept[2]));
+            }
+            close_sub();
+        }
+        lvl_to_sub[nlevels] = (uint32_t)sub_off.size() - 1;
+        if (c.coeffs.size() >= (1u << 30)) {
+            *why_not = "coefficient table too large";
+            return G16_OK;
+        }
+        G16_TRY(upload(sub_off, &d_sub_off, st));
+        G16_TRY(upload(prod_off, &d_prod_off, st));
+        G16_TRY(upload(prods, &d_prods, st));
+        G16_TRY(upload(ops, &d_ops, st));
+        G16_TRY(upload(rec2, &d_rec2, st));
+    }
     std::vector<uint4> rec(2 * lvl_instr.size());
     for (size_t k = 0; k < lvl_instr.size(); k++) {
         const uint32_t ins = lvl_instr[k];
@@ -673,6 +830,7 @@ int GpuSolverPlan::run(const Fr* d_coeffs, int unit_ids, Fr* d_wires, size_t wst
                                                               lvl_end, unit_ids, d_err);
     else {
         static const bool no_narrow = getenv("G16_SOLVER_NARROW") && atoi(getenv("G16_SOLVER_NARROW")) == 0;
+        static const bool tpi_kernel = getenv("G16_SOLVER_TPI") && atoi(getenv("G16_SOLVER_TPI")) != 0;   // lanes-per-row kernel
         static const bool trace_sync = getenv("G16_TRACE_SYNC") && atoi(getenv("G16_TRACE_SYNC")) != 0;
         for (const Segment& sg : segments) {
             const uint32_t lo = std::max(sg.begin, lvl_begin), hi = std::min(sg.end, lvl_end);
@@ -685,6 +843,10 @@ int GpuSolverPlan::run(const Fr* d_coeffs, int unit_ids, Fr* d_wires, size_t wst
                 k_solve_narrow<<<cdiv(B, NARROW_THREADS), NARROW_THREADS, 0, st>>>(d_lvl_off, d_rec, d_calldata, d_coeffs,
                                                                                   d_coeff_invs, d_wires, wstride, nw + X_BLINDER,
                                                                                   lo, hi, unit_ids, d_err, (uint32_t)B);
+            else if (!tpi_kernel)
+                k_solve_2p<<<(unsigned)B, SOLVE2_THREADS, 0, st>>>(d_sub_off, d_prod_off, d_prods, d_rec2, d_ops, d_calldata, d_coeffs,
+                                                                   d_coeff_invs, d_wires, wstride, nw + X_BLINDER, lvl_to_sub[lo],
+                                                                   lvl_to_sub[hi], unit_ids, d_err);
             else
                 k_solve_tpi<<<(unsigned)B, SOLVE_TT, 0, st>>>(d_lvl_off, d_rec, d_calldata, d_coeffs, d_coeff_invs, d_wires,
                                                               wstride, nw + X_BLINDER, lo, hi, unit_ids, d_err);

@@ -20,6 +20,11 @@ struct GpuSolverPlan {
     uint32_t *d_lvl_off = nullptr, *d_lvl_instr = nullptr, *d_instr_cd = nullptr, *d_calldata = nullptr;
     uint4* d_info = nullptr;
     uint4* d_rec = nullptr;                 // flattened plan: two uint4 per instruction, in level order
+    // two-phase plan (k_solve_2p): levels split into sub-levels of bounded product count
+    uint32_t *d_sub_off = nullptr, *d_prod_off = nullptr;   // sub-level -> row range / product range
+    uint2 *d_prods = nullptr, *d_ops = nullptr;             // (coefficient id, wire) per product; (code, ref) per operand
+    uint4* d_rec2 = nullptr;                                // per row: (mode, wire, coefficient code, row), (first operand, nL, nR, nO)
+    std::vector<uint32_t> lvl_to_sub;                       // level -> first sub-level (size nlevels + 1)
     Fr* d_coeff_invs = nullptr;
     // Hints that work over the integers (emulated.mulHint, the sw-grumpkin scalar split) have no device version; when
     // their inputs only depend on the circuit's inputs (and on each other) the host evaluates them per proof before

@@ -638,9 +638,14 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
     c->max_batch = max_batch;
     // the solver is latency-bound (one CTA per proof walks ~10^3 levels): give it 4 proving batches at a
     // time so its latency hides behind the proving of the previous group
-    const size_t group_chunks = getenv("G16_SOLVE_GROUP") ? std::max(1l, atol(getenv("G16_SOLVE_GROUP"))) : 4;
+    // Stage A solves a GROUP of chunks at once (the solver is latency-bound: 512 proofs take little longer than 64) while
+    // the previous group is proved.  8 chunks per group keep its latency under load (25-55 ms) far from the group's
+    // proving time (140-210 ms); the first group of a call is 4 chunks, since nothing can be proved before it is solved.
+    const size_t group_chunks = getenv("G16_SOLVE_GROUP") ? std::max(1l, atol(getenv("G16_SOLVE_GROUP"))) : 8;
+    const size_t first_chunks = getenv("G16_SOLVE_FIRST") ? std::max(1l, atol(getenv("G16_SOLVE_FIRST"))) : 4;
     const size_t solve_batch = max_batch >= 8 ? group_chunks * max_batch : max_batch;
     c->solve_batch = solve_batch;
+    c->first_group = max_batch >= 8 ? std::min(first_chunks, group_chunks) * max_batch : max_batch;
     // ---- bases -------------------------------------------------------------------------------
     auto win = [&](size_t npts) { return msm_pick_window(npts, max_batch); };
     G16_TRY(c->bA.load(basesA.data(), basesA.size(), win(basesA.size()), 1, st));
@@ -730,7 +735,20 @@ int g16_circuit_load(g16_ctx* ctx, const uint8_t* ccs, size_t ccs_len, const uin
     }
     const NttDomain* dom;
     G16_TRY(ctx->ntt.domain(c->logn, st, &dom));
-    G16_CUDA(cudaStreamSynchronize(st));
+    G16_CUDA(cudaStreamSynchronize(st));   // key tables and maps are in place
+    if (c->plan.valid) {
+        // size what stage A grows on first use (a cudaFree in the middle of a pipelined call drains the device):
+        // the commitment MSM's scratch for a full group (zero wires: no bucket entries) and the hint outputs
+        g16_circuit::Slot& sl = c->slots[0];
+        if (c->plan.commit_level != (uint32_t)-1 && c->n_committed) {
+            G16_CUDA(cudaMemsetAsync(sl.d_wires.ptr, 0, sizeof(Fr) * c->wstride * solve_batch, c->aux_stream));
+            G16_TRY(c->g1_aux.run(c->bCommit, (const Fr*)sl.d_wires.ptr, c->wstride, c->d_map_commit, 1, solve_batch,
+                                  (G1Affine*)sl.d_commit_out.ptr, c->aux_stream));
+        }
+        for (auto& s2 : c->slots)
+            if (!c->plan.host_wires.empty()) G16_TRY(s2.d_pre.ensure(sizeof(Fr) * c->plan.host_wires.size() * solve_batch));
+        G16_CUDA(cudaStreamSynchronize(c->aux_stream));
+    }
     ctx->circuits.push_back(c.get());
     *out = c.release();
     return G16_OK;
@@ -1190,9 +1208,15 @@ template <class Launch, class After>
 static int run_pipeline(g16_circuit* c, size_t n, Launch launch, uint8_t* proofs, After after) {
     cudaStream_t st = c->ctx->stream;
     const size_t plen = c->has_commitment ? 388 : 324;
-    const size_t SB = c->solve_batch;
-    const size_t ngroups = (n + SB - 1) / SB;
-    auto group_size = [&](size_t g) { return std::min(SB, n - g * SB); };
+    // group schedule: the first group is small (nothing can be proved before it is solved), the others fill the slot
+    const size_t SB = c->solve_batch, SB0 = std::min(SB, c->first_group);
+    std::vector<size_t> gfirst(1, 0);
+    for (size_t at = 0; at < n;) {
+        at += std::min(gfirst.size() == 1 ? SB0 : SB, n - at);
+        gfirst.push_back(at);
+    }
+    const size_t ngroups = gfirst.size() - 1;
+    auto group_size = [&](size_t g) { return gfirst[g + 1] - gfirst[g]; };
     struct Pending {
         bool live = false;
         size_t first = 0, B = 0, off = 0;
@@ -1213,7 +1237,7 @@ static int run_pipeline(g16_circuit* c, size_t n, Launch launch, uint8_t* proofs
         after(pend.first, pend.B);
         return G16_OK;
     };
-    std::future<StageResult> fut = launch((size_t)0);
+    std::future<StageResult> fut = launch((size_t)0, gfirst[0], group_size(0));
     int total_launches = 0, rc = G16_OK;
     size_t chunk_no = 0;
     for (size_t g = 0; g < ngroups && rc == G16_OK; g++) {
@@ -1225,7 +1249,7 @@ static int run_pipeline(g16_circuit* c, size_t n, Launch launch, uint8_t* proofs
         }
         // the slot stage g+1 writes was last read by the chunk that may still be in flight
         if ((rc = drain()) != G16_OK) break;
-        if (g + 1 < ngroups) fut = launch(g + 1);   // stage A of group g+1 runs while the device proves group g
+        if (g + 1 < ngroups) fut = launch(g + 1, gfirst[g + 1], group_size(g + 1));   // stage A of group g+1 runs while the device proves group g
         g16_circuit::Slot& sl = c->slots[g & 1];
         const size_t G = group_size(g);
         if (cudaStreamWaitEvent(st, sl.ready, 0) != cudaSuccess) {
@@ -1233,7 +1257,7 @@ static int run_pipeline(g16_circuit* c, size_t n, Launch launch, uint8_t* proofs
             set_error("cudaStreamWaitEvent failed");
         }
         for (size_t off = 0; off < G && rc == G16_OK; off += c->max_batch) {
-            const size_t B = std::min(c->max_batch, G - off), first = g * SB + off;
+            const size_t B = std::min(c->max_batch, G - off), first = gfirst[g] + off;
             const int ring = (int)(chunk_no++ & 1);
             trace("pipeline: chunk begin", (long)first);
             int p = 0;
@@ -1276,11 +1300,9 @@ int g16_prove_wires(g16_circuit* c, size_t n, const uint8_t* wires_be, const uin
     G16_CUDA(cudaSetDevice(c->ctx->device));
     G16_LOCK(c->ctx);
     if (c->world > 1) return prove_wires_sync(c, n, wires_be, rnd, proofs);
-    const size_t SB = c->solve_batch;
-    auto launch = [&](size_t g) {
-        const size_t first = g * SB;
-        return std::async(std::launch::async, stage_wires, c, (int)(g & 1), std::min(SB, n - first),
-                          wires_be + first * c->nw * 32, rnd ? rnd + 96 * first : nullptr, first);
+    auto launch = [&](size_t g, size_t first, size_t G) {
+        return std::async(std::launch::async, stage_wires, c, (int)(g & 1), G, wires_be + first * c->nw * 32,
+                          rnd ? rnd + 96 * first : nullptr, first);
     };
     return run_pipeline(c, n, launch, proofs, [](size_t, size_t) {});
 }
@@ -1311,10 +1333,8 @@ int g16_prove_batch(g16_circuit* c, size_t n, const uint8_t* assignments_be, siz
     }
     // groups of solve_batch proofs are solved together (stage A); each group is proved in chunks of
     // max_batch (stage B) while the next group is being solved
-    const size_t SB = c->solve_batch;
     const bool solve_overlap = !(getenv("G16_SOLVE_OVERLAP") && atoi(getenv("G16_SOLVE_OVERLAP")) == 0);
-    auto launch = [&](size_t g) {
-        const size_t first = g * SB, G = std::min(SB, n - first);
+    auto launch = [&](size_t g, size_t first, size_t G) {
         if (c->plan.valid)   // G16_SOLVE_OVERLAP=0 runs the device solver between groups instead of beside them
             return std::async(solve_overlap ? std::launch::async : std::launch::deferred, stage_solve_gpu, c, (int)(g & 1), G,
                               assignments_be + first * nin * 32, rnd ? rnd + 96 * first : nullptr, first, false);

@@ -49,6 +49,7 @@ struct g16_circuit {
     size_t wstride = 0;     // nw + X_COUNT
     size_t max_batch = 0;      // proofs per device proving batch
     size_t solve_batch = 0;    // proofs per witness-solve batch (a multiple of max_batch)
+    size_t first_group = 0;   // proofs in the first group of a call (<= solve_batch)
     bool has_commitment = false;
     int unit_ids = 0;       // coefficient ids 0/1/3 are 0/+1/-1 (gnark's fixed table prefix)
     size_t n_committed = 0;        // committed wires held by THIS rank (all of them unless the circuit is split)
