@@ -823,14 +823,14 @@ int GpuSolverPlan::assign(const uint8_t* d_asg_be, const uint8_t* d_rnd_be, uint
 int GpuSolverPlan::run(const Fr* d_coeffs, int unit_ids, Fr* d_wires, size_t wstride, size_t nw, size_t B,
                        uint32_t lvl_begin, uint32_t lvl_end, uint32_t* d_err, cudaStream_t st) const {
     if (lvl_begin >= lvl_end) return G16_OK;
-    static const bool cta_per_proof = getenv("G16_SOLVER_CTA") && atoi(getenv("G16_SOLVER_CTA")) != 0;   // round-1 kernel
+    const bool cta_per_proof = getenv("G16_SOLVER_CTA") && atoi(getenv("G16_SOLVER_CTA")) != 0;   // round-1 kernel
     if (cta_per_proof)
         k_solve_levels<<<(unsigned)B, SOLVE_THREADS, 0, st>>>(d_lvl_off, d_lvl_instr, d_info, d_instr_cd, d_calldata, d_coeffs,
                                                               d_coeff_invs, d_wires, wstride, nw + X_BLINDER, lvl_begin,
                                                               lvl_end, unit_ids, d_err);
     else {
-        static const bool no_narrow = getenv("G16_SOLVER_NARROW") && atoi(getenv("G16_SOLVER_NARROW")) == 0;
-        static const bool tpi_kernel = getenv("G16_SOLVER_TPI") && atoi(getenv("G16_SOLVER_TPI")) != 0;   // lanes-per-row kernel
+        const bool no_narrow = getenv("G16_SOLVER_NARROW") && atoi(getenv("G16_SOLVER_NARROW")) == 0;
+        const bool tpi_kernel = getenv("G16_SOLVER_TPI") && atoi(getenv("G16_SOLVER_TPI")) != 0;   // lanes-per-row kernel
         static const bool trace_sync = getenv("G16_TRACE_SYNC") && atoi(getenv("G16_TRACE_SYNC")) != 0;
         for (const Segment& sg : segments) {
             const uint32_t lo = std::max(sg.begin, lvl_begin), hi = std::min(sg.end, lvl_end);

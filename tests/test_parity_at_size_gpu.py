@@ -163,7 +163,7 @@ def test_real_withdraw_circuit_shape_on_gpu(ctx):
 
 
 def test_device_solver_equals_host_solver_audit_like(audit):
-    """The batched device witness solver (k_solve_tpi, what g16_prove_batch uses) and the C++ host solver agree on
+    """The batched device witness solver (what g16_prove_batch uses) and the C++ host solver agree on
     every wire of a full group of audit_like witnesses (two-phase solve, commitment MSM and challenge in between)."""
     sc, circ, orc, vk = audit
     n = 70                                              # more than one device batch, ragged
@@ -171,6 +171,36 @@ def test_device_solver_equals_host_solver_audit_like(audit):
     rnd = b"".join(rnd_for(300 + i) for i in range(n))
     assert circ.solver == "gpu"
     assert circ.witness_batch_dev(asg, n, rnd) == circ.witness_batch(asg, n, rnd)
+
+
+def test_device_solver_kernels_agree(ctx, audit, monkeypatch):
+    """Every device solver kernel yields the same wires as the host solver, on both benchmark circuits: the default
+    (k_solve_2p for wide levels + k_solve_narrow for runs of thin levels -- the division chain at the end of the
+    withdraw circuit), without the thread-per-proof kernel, the lanes-per-row kernel (k_solve_tpi) and the round-1
+    thread-per-row kernel (k_solve_levels)."""
+    import json
+    sc, circ_a, _orc, _vk = audit
+    n = 37                                              # ragged: not a multiple of a warp
+    asg_a = b"".join(sc.assignment_bytes(9100 + i) for i in range(n))
+    raw = open(os.path.join(GOLD, "shielded_pool_verifier.ccs"), "rb").read()
+    meta = json.load(open(os.path.join(GOLD, "withdraw_assignments.json")))
+    blob = open(os.path.join(GOLD, "withdraw_assignments.bin"), "rb").read()
+    nb = meta["n_values"] * 32
+    asg_w = b"".join(blob[(i % meta["n"]) * nb:(i % meta["n"] + 1) * nb] for i in range(n))
+    pk, _ = ctx.setup(raw, b"withdraw-solver-kernels")
+    circ_w = ctx.load_circuit(raw, pk)
+    rnd = b"".join(rnd_for(900 + i) for i in range(n))
+    for circ, asg in ((circ_a, asg_a), (circ_w, asg_w)):
+        assert circ.solver == "gpu"
+        want = circ.witness_batch(asg, n, rnd)          # host solver
+        for env in ({}, {"G16_SOLVER_NARROW": "0"}, {"G16_SOLVER_TPI": "1"}, {"G16_SOLVER_TPI": "1", "G16_SOLVER_NARROW": "0"},
+                    {"G16_SOLVER_CTA": "1"}):
+            for k in ("G16_SOLVER_NARROW", "G16_SOLVER_TPI", "G16_SOLVER_CTA"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            assert circ.witness_batch_dev(asg, n, rnd) == want, env
+    circ_w.free()
 
 
 def test_withdraw_circuit_solves_on_the_device(ctx, monkeypatch):
