@@ -322,8 +322,11 @@ k_vb_order(const uint32_t* __restrict__ vb_size, const uint32_t* __restrict__ nv
 #ifndef MSM_ACC_MIN_CTAS
 #define MSM_ACC_MIN_CTAS 4   // 128 registers; 5 (96 registers, small spills) measured no faster: the wide-multiplier pipe is the limit, not occupancy
 #endif
+#ifndef MSM_ACC_G2_MIN_CTAS
+#define MSM_ACC_G2_MIN_CTAS 1
+#endif
 template <class F>
-__global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fp) ? MSM_ACC_MIN_CTAS : 1)
+__global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fp) ? MSM_ACC_MIN_CTAS : MSM_ACC_G2_MIN_CTAS)
 k_msm_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ entries,
                  const uint32_t* __restrict__ vb_start, const uint32_t* __restrict__ vb_size,
                  const uint32_t* __restrict__ order, const uint32_t* __restrict__ nv_total,
