@@ -92,6 +92,15 @@ class ClockSampler(threading.Thread):
 _REAL_STDOUT = None
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_accumulate_dram_traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_launch_avg"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def quiet_stdout():
     """stdout carries exactly ONE line (the JSON record): anything a library prints there at the C level (NCCL's
     version banner at communicator creation, for one) is sent to stderr instead."""
@@ -535,7 +544,9 @@ def main():
             "gpu_launches": results["launches"],
             "roofline": {"bound": "imad", "kernel": "k_msm_accumulate (G1+G2 bucket accumulation)",
                          "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
-                         "frac": achieved / (imad_peak / 1e12) if imad_peak else None, "traffic": None,
+                         "frac": achieved / (imad_peak / 1e12) if imad_peak else None, "traffic": ncu_traffic(),
+                         "traffic_source": "profiles/r02_accumulate_dram_traffic.json: average dram read+write bytes per accumulate "
+                                           "launch of one 64-proof withdraw chunk, one ncu --set full capture (not live)",
                          "peak_source": "measured in this run: g16_measure_imad_peak(IMAD); IMAD.WIDE.U32.X issues at %.2f T/s, "
                                         "FP64 FMA at %.2f T/s" % (imadw_peak / 1e12, dfma_peak / 1e12),
                          "kernel_ms_per_step": acc_ms / args.steps, "kernel_share_of_step": acc_ms / results["dev_serial"],
