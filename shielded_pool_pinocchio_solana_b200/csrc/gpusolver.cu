@@ -524,6 +524,7 @@ void GpuSolverPlan::release() {
     host_wires.clear();
     host_inputs.clear();
     segments.clear();
+    commit_hashed.clear();
     d_lvl_off = d_lvl_instr = d_instr_cd = d_calldata = nullptr;
     d_info = nullptr;
     d_coeff_invs = nullptr;
@@ -587,9 +588,26 @@ int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not
                         *why_not = "more than one commitment";
                         return G16_OK;
                     }
-                    if (!c.commitments[0].public_and_commitment_committed.empty()) {
-                        *why_not = "commitment hashes public wires (not needed by the reference circuits)";
-                        return G16_OK;
+                    // public wires committed to (api.Commit over public inputs): hashed into the challenge on the host
+                    // next to the commitment point; their expressions must hang off the circuit's inputs
+                    {
+                        const size_t nh = c.commitments[0].public_and_commitment_committed.size();
+                        if (nin < 1 + nh) {
+                            *why_not = "commitment hint with fewer inputs than hashed wires";
+                            return G16_OK;
+                        }
+                        commit_hashed.assign(nh, {});
+                        size_t q = 3 + 1 + 2 * (size_t)cd[3];   // input 0 is the commitment's index
+                        for (size_t h = 0; h < nh; h++) {
+                            const uint32_t ln = cd[q++];
+                            for (uint32_t t = 0; t < ln; t++, q += 2) {
+                                if (cd[q + 1] != CCS_CONST_WIRE && cd[q + 1] >= c.nb_public + c.nb_secret) {
+                                    *why_not = "commitment hashes a solved wire";
+                                    return G16_OK;
+                                }
+                                commit_hashed[h].push_back({cd[q], cd[q + 1]});
+                            }
+                        }
                     }
                     commit_level = (uint32_t)lv;
                     commit_wire = o0;

@@ -1,6 +1,7 @@
 // gpusolver.cuh -- batched R1CS witness solver on the GPU (see gpusolver.cu).
 #pragma once
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "ccs.hpp"
@@ -17,6 +18,8 @@ struct GpuSolverPlan {
     uint32_t nlevels = 0;
     uint32_t commit_level = (uint32_t)-1;   // level holding the BSB22 commitment hint, or -1
     uint32_t commit_wire = 0;
+    // linear expressions over INPUT wires whose values are hashed into the challenge after the commitment point
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> commit_hashed;   // (coefficient id, wire)
     uint32_t *d_lvl_off = nullptr, *d_lvl_instr = nullptr, *d_instr_cd = nullptr, *d_calldata = nullptr;
     uint4* d_info = nullptr;
     uint4* d_rec = nullptr;                 // flattened plan: two uint4 per instruction, in level order

@@ -1115,10 +1115,21 @@ static StageResult stage_solve_gpu(g16_circuit* c, int slot_id, size_t B, const 
         G16_STAGE_CUDA(cudaMemcpyAsync(sl.commits.data(), sl.d_commit_out.ptr, sizeof(G1Affine) * B, cudaMemcpyDeviceToHost, st));
         G16_STAGE_CUDA(cudaStreamSynchronize(st));
         trace("solve_gpu: phase1 done");
+        const auto& hashed = c->plan.commit_hashed;
+        std::vector<uint8_t> msg(64 + 32 * hashed.size());
         for (size_t b = 0; b < B; b++) {
-            uint8_t msg[64];
-            g1_to_be(sl.commits[b], msg);
-            h_chal[b] = hash_to_fr(msg, 64, "bsb22-commitment");
+            g1_to_be(sl.commits[b], msg.data());
+            for (size_t h = 0; h < hashed.size(); h++) {   // committed public wires, from the caller's assignment
+                HFr v = HFr::zero();
+                for (const auto& term : hashed[h]) {
+                    const HFr x = term.second == CCS_CONST_WIRE || term.second == 0
+                                      ? HFr::one()
+                                      : HFr::from_be(assignments_be + (b * nin + term.second - 1) * 32);
+                    v = v + circ.coeffs[term.first] * x;
+                }
+                v.to_be(msg.data() + 64 + 32 * h);
+            }
+            h_chal[b] = hash_to_fr(msg.data(), msg.size(), "bsb22-commitment");
         }
         trace("solve_gpu: challenges hashed");
         G16_STAGE_CUDA(cudaMemcpyAsync(sl.d_chal.ptr, h_chal, sizeof(Fr) * B, cudaMemcpyHostToDevice, st));

@@ -126,7 +126,7 @@ class SyntheticCircuit:
 
 
 def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=48, seed=0xA0D17,
-          dens_b=5, frac_c2=0.31, n_coeffs=256, div_zero=False, value_mix=None):
+          dens_b=5, frac_c2=0.31, n_coeffs=256, div_zero=False, value_mix=None, n_public_committed=0):
     """`value_mix` = (zero, one, small, uniform) fractions: body rows are then drawn from four kinds whose SOLVED
     wire is a balanced bit (xor of two bits), a zero (b * (1 - b)), a byte (sum of 2^k * bit) or a uniform field
     element, and the secret inputs past the first 8 are bits / bytes / uniform values in matching proportions --
@@ -310,11 +310,13 @@ def build(n_constraints, n_public=2, n_secret=64, commitment=True, n_committed=4
     if commitment:
         (blinder,) = add_hint(H_RANDOMIZE, [], 1)
         committed = body_wires[:n_committed] + [blinder]
-        (cw,) = add_hint(H_COMMIT, [[(0, CONST_WIRE)]] + [[(1, w)] for w in committed], 1)
+        # gnark api.Commit over public wires too: their values are hashed into the challenge next to the commitment
+        pub_committed = [PUB(i) for i in range(min(n_public_committed, n_public))]
+        (cw,) = add_hint(H_COMMIT, [[(0, CONST_WIRE)]] + [[(1, w)] for w in pub_committed] + [[(1, w)] for w in committed], 1)
         known.append(cw)
         # the challenge must feed later rows or it would be dead weight
-        commit_info = {"CommitmentIndex": cw, "PrivateCommitted": committed, "NbPublicCommitted": 0,
-                       "PublicAndCommitmentCommitted": []}
+        commit_info = {"CommitmentIndex": cw, "PrivateCommitted": committed, "NbPublicCommitted": len(pub_committed),
+                       "PublicAndCommitmentCommitted": pub_committed}
         new = next_wire
         next_wire += 1
         add_r1c([(1, cw)], [(1, cw), (rng.randrange(5, 5 + n_coeffs), body_wires[0])], [(1, new)], defines=new)

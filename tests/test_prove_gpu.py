@@ -115,6 +115,38 @@ def test_audit_like_circuit_proves_and_verifies(ctx):
     circ.free()
 
 
+def test_commitment_over_public_wires_device_path(ctx):
+    """A commitment that also covers public inputs takes the DEVICE solver: the committed public values are hashed
+    into the challenge on the host from the caller's assignment.  GPU setup = oracle setup (same seed), so the proof
+    bytes must equal the oracle's; the product's verifier accepts them and rejects a changed committed input."""
+    import hashlib
+    import bn254 as B
+    import ccs
+    import groth16 as G
+    import serialize as S
+    from shielded_pool_pinocchio_solana_b200 import synth
+    sc = synth.build(120, n_public=3, n_secret=16, n_committed=8, seed=11, n_public_committed=2)
+    c = ccs.parse_ccs(sc.ccs)
+    opk, ovk, _tx = G.setup(c, b"pubcommit")
+    pk, vk = ctx.setup(sc.ccs, b"pubcommit")
+    assert pk == G.write_pk(opk) and vk == G.write_vk(ovk)
+    circ = ctx.load_circuit(sc.ccs, pk)
+    assert circ.solver == "gpu", circ.solver
+    enc = lambda v: b"".join(S.fr_to_bytes(x) for x in v)
+    n = 3
+    asgs = [sc.assignment(5 + i) for i in range(n)]
+    rnds = [[int.from_bytes(hashlib.sha256(b"pubcommit/%d/%d" % (i, k)).digest(), "big") % B.R for k in range(3)] for i in range(n)]
+    proofs, pws = circ.prove_batch(b"".join(enc(a) for a in asgs), n, b"".join(enc(x) for x in rnds))
+    for i in range(n):
+        want_proof, want_pw, _aux = G.prove(c, opk, asgs[i], *rnds[i])
+        assert proofs[i] == want_proof and pws[i] == want_pw, "proof %d" % i
+        assert g16.verify(vk, proofs[i], pws[i]) is True
+    bad = bytearray(pws[0])
+    bad[12 + 31] ^= 1
+    assert g16.verify(vk, proofs[0], bytes(bad)) is False
+    circ.free()
+
+
 def test_gpu_and_host_solver_agree(ctx, golden, circuit, monkeypatch):
     """The batched device solver (default) and the C++ host solver give the same proof bytes."""
     assert circuit.solver == "gpu"

@@ -82,3 +82,33 @@ def test_cli_verify_exit_codes(golden, tmp_path):
     bad = subprocess.run([exe, "verify", str(tmp_path / "c.vk"), str(tmp_path / "c.proof"), str(tmp_path / "bad.pw")],
                          capture_output=True)
     assert bad.returncode == 1 and b"rejected" in bad.stderr
+
+
+def test_commitment_over_public_wires():
+    """gnark api.Commit over PUBLIC inputs (CommitmentInfo.PublicAndCommitmentCommitted non-empty): their values are
+    hashed into the challenge after the commitment point (gnark backend/groth16/bn254/{prove,verify}.go).  The
+    reference circuits commit to private wires only; this pins the general form on a synthetic circuit: oracle proof
+    -> oracle verifier and the product's verifier accept, a changed committed public input is rejected, and the C++
+    host solver reproduces the oracle's wires."""
+    import hashlib
+    import ccs
+    from shielded_pool_pinocchio_solana_b200 import synth
+    sc = synth.build(120, n_public=3, n_secret=16, n_committed=8, seed=11, n_public_committed=2)
+    c = ccs.parse_ccs(sc.ccs)
+    assert tuple(c.commitments[0]["PublicAndCommitmentCommitted"]) == (1, 2)
+    pk, vk, tx = G.setup(c, b"pubcommit")
+    asg = sc.assignment(5)
+    r, s, bl = [int.from_bytes(hashlib.sha256(b"pubcommit/%d" % k).digest(), "big") % B.R for k in range(3)]
+    proof, pw, aux = G.prove(c, pk, asg, r, s, bl)
+    assert G.verify(vk, proof, pw) and G.closed_form_check(c, tx, aux["wires"], proof, r, s)
+    vkb = G.write_vk(vk)
+    assert g16.verify(vkb, proof, pw) is True
+    bad = bytearray(pw)
+    bad[12 + 31] ^= 1                                   # first public input, one of the two hashed ones
+    assert g16.verify(vkb, proof, bytes(bad)) is False and G.verify(vk, proof, bytes(bad)) is False
+    enc = lambda v: b"".join(S.fr_to_bytes(x) for x in v)
+    cw = c.commitments[0]["CommitmentIndex"]
+    wires, _ = g16.solve_assignment(sc.ccs, enc(asg), c.nb_wires, blinder_be=S.fr_to_bytes(bl),
+                                    challenges_be=S.fr_to_bytes(aux["wires"][cw]),
+                                    n_committed=len(c.commitments[0]["PrivateCommitted"]))
+    assert wires == enc(aux["wires"])
