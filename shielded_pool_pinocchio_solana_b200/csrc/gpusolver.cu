@@ -311,14 +311,19 @@ k_solve_tpi(const uint32_t* __restrict__ lvl_off, const uint4* __restrict__ rec,
 // independent).  Two barriers per sub-level.
 constexpr int SOLVE2_THREADS = 128;
 constexpr uint32_t SOLVE2_PRODUCTS = 1024;   // 32 KB of shared memory
-enum : uint32_t { OPD_PRODUCT = 0, OPD_PLUS = 1, OPD_CONST = 2, OPD_MINUS = 3 };
+enum : uint32_t { OPD_PRODUCT = 0, OPD_PLUS = 1, OPD_CONST = 2, OPD_MINUS = 3, OPD_INLINE = 4 };
 
 __device__ __forceinline__ Fr side_sum(const uint2* __restrict__ ops, uint32_t n, const Fr* w, const Fr* __restrict__ coeffs,
-                                       const Fr* prod) {
+                                       const Fr* prod, const uint2* __restrict__ inline_prods) {
     Fr acc = Fr::zero();
 #pragma unroll 2
     for (uint32_t i = 0; i < n; i++) {
         const uint2 d = ops[i];
+        if (d.x == OPD_INLINE) {   // a row with more products than the shared buffer holds multiplies in place
+            const uint2 pr = inline_prods[d.y];
+            acc = acc + coeffs[pr.x] * w[pr.y];
+            continue;
+        }
         const Fr* src = d.x == OPD_PRODUCT ? prod + d.y : (d.x == OPD_CONST ? coeffs + d.y : w + d.y);
         const Fr v = *src;
         acc = acc + (d.x == OPD_MINUS ? v.neg() : v);
@@ -328,8 +333,8 @@ __device__ __forceinline__ Fr side_sum(const uint2* __restrict__ ops, uint32_t n
 
 __global__ void __launch_bounds__(SOLVE2_THREADS, 4)
 k_solve_2p(const uint32_t* __restrict__ sub_off, const uint32_t* __restrict__ prod_off, const uint2* __restrict__ prods,
-           const uint4* __restrict__ rec, const uint2* __restrict__ ops, const uint32_t* __restrict__ calldata,
-           const Fr* __restrict__ coeffs, const Fr* __restrict__ coeff_invs, Fr* wires, size_t wstride, size_t blinder_slot,
+           const uint4* __restrict__ rec, const uint2* __restrict__ ops, const uint2* __restrict__ inline_prods,
+           const uint32_t* __restrict__ calldata, const Fr* __restrict__ coeffs, const Fr* __restrict__ coeff_invs, Fr* wires, size_t wstride, size_t blinder_slot,
            uint32_t sub_begin, uint32_t sub_end, int unit_ids, uint32_t* err) {
     __shared__ Fr prod[SOLVE2_PRODUCTS];
     const uint32_t b = blockIdx.x;
@@ -350,9 +355,9 @@ k_solve_2p(const uint32_t* __restrict__ sub_off, const uint32_t* __restrict__ pr
                 continue;
             }
             const uint2* o = ops + shp.x;
-            const Fr L = side_sum(o, shp.y, w, coeffs, prod);
-            const Fr Rr = side_sum(o + shp.y, shp.z, w, coeffs, prod);
-            const Fr O = side_sum(o + shp.y + shp.z, shp.w, w, coeffs, prod);
+            const Fr L = side_sum(o, shp.y, w, coeffs, prod, inline_prods);
+            const Fr Rr = side_sum(o + shp.y, shp.z, w, coeffs, prod, inline_prods);
+            const Fr O = side_sum(o + shp.y + shp.z, shp.w, w, coeffs, prod, inline_prods);
             if (inf.x == 0) {
                 if (L * Rr != O) atomicMin(e, inf.w + 1);           // constraint row (1-based)
             } else if (inf.x == 1) {
@@ -513,9 +518,9 @@ void GpuSolverPlan::release() {
     cudaFree(d_coeff_invs);
     cudaFree(d_rec);
     d_rec = nullptr;
-    cudaFree(d_sub_off); cudaFree(d_prod_off); cudaFree(d_prods); cudaFree(d_ops); cudaFree(d_rec2);
+    cudaFree(d_sub_off); cudaFree(d_prod_off); cudaFree(d_prods); cudaFree(d_ops); cudaFree(d_rec2); cudaFree(d_iprods);
     d_sub_off = d_prod_off = nullptr;
-    d_prods = d_ops = nullptr;
+    d_prods = d_ops = d_iprods = nullptr;
     d_rec2 = nullptr;
     lvl_to_sub.clear();
     cudaFree(d_host_wires);
@@ -737,7 +742,7 @@ int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not
     {
         const HFr one = HFr::one(), minus_one = HFr::one().neg();
         std::vector<uint32_t> sub_off(1, 0), prod_off(1, 0);
-        std::vector<uint2> prods, ops;
+        std::vector<uint2> prods, ops, iprods;
         std::vector<uint4> rec2;
         lvl_to_sub.assign(nlevels + 1, 0);
         for (uint32_t lv = 0; lv < nlevels; lv++) {
@@ -764,11 +769,8 @@ int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not
                     if (wid != unk && wid != CCS_CONST_WIRE && !c.coeffs[cid].is_zero() && !(c.coeffs[cid] == one) && !(c.coeffs[cid] == minus_one))
                         row_products++;
                 }
-                if (row_products > SOLVE2_PRODUCTS) {
-                    *why_not = "a row with more than " + std::to_string(SOLVE2_PRODUCTS) + " non-unit terms";
-                    return G16_OK;
-                }
-                if (in_sub + row_products > SOLVE2_PRODUCTS) close_sub();
+                const bool inline_row = row_products > SOLVE2_PRODUCTS;   // multiplies in place, thread per row
+                if (!inline_row && in_sub + row_products > SOLVE2_PRODUCTS) close_sub();
                 uint32_t kept[3] = {0, 0, 0};
                 const uint32_t first_op = (uint32_t)ops.size();
                 size_t p = 4;
@@ -781,7 +783,10 @@ int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not
                         if (wid == CCS_CONST_WIRE) ops.push_back(make_uint2(OPD_CONST, cid));
                         else if (cf == one) ops.push_back(make_uint2(OPD_PLUS, wid));
                         else if (cf == minus_one) ops.push_back(make_uint2(OPD_MINUS, wid));
-                        else {
+                        else if (inline_row) {
+                            ops.push_back(make_uint2(OPD_INLINE, (uint32_t)iprods.size()));
+                            iprods.push_back(make_uint2(cid, wid));
+                        } else {
                             ops.push_back(make_uint2(OPD_PRODUCT, in_sub++));
                             prods.push_back(make_uint2(cid, wid));
                         }
@@ -806,6 +811,7 @@ int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not
         G16_TRY(upload(sub_off, &d_sub_off, st));
         G16_TRY(upload(prod_off, &d_prod_off, st));
         G16_TRY(upload(prods, &d_prods, st));
+        G16_TRY(upload(iprods, &d_iprods, st));
         G16_TRY(upload(ops, &d_ops, st));
         G16_TRY(upload(rec2, &d_rec2, st));
     }
@@ -862,7 +868,7 @@ int GpuSolverPlan::run(const Fr* d_coeffs, int unit_ids, Fr* d_wires, size_t wst
                                                                                   d_coeff_invs, d_wires, wstride, nw + X_BLINDER,
                                                                                   lo, hi, unit_ids, d_err, (uint32_t)B);
             else if (!tpi_kernel)
-                k_solve_2p<<<(unsigned)B, SOLVE2_THREADS, 0, st>>>(d_sub_off, d_prod_off, d_prods, d_rec2, d_ops, d_calldata, d_coeffs,
+                k_solve_2p<<<(unsigned)B, SOLVE2_THREADS, 0, st>>>(d_sub_off, d_prod_off, d_prods, d_rec2, d_ops, d_iprods, d_calldata, d_coeffs,
                                                                    d_coeff_invs, d_wires, wstride, nw + X_BLINDER, lvl_to_sub[lo],
                                                                    lvl_to_sub[hi], unit_ids, d_err);
             else

@@ -26,6 +26,7 @@ struct GpuSolverPlan {
     // two-phase plan (k_solve_2p): levels split into sub-levels of bounded product count
     uint32_t *d_sub_off = nullptr, *d_prod_off = nullptr;   // sub-level -> row range / product range
     uint2 *d_prods = nullptr, *d_ops = nullptr;             // (coefficient id, wire) per product; (code, ref) per operand
+    uint2* d_iprods = nullptr;                              // products of rows too long for the shared buffer (multiplied in place)
     uint4* d_rec2 = nullptr;                                // per row: (mode, wire, coefficient code, row), (first operand, nL, nR, nO)
     std::vector<uint32_t> lvl_to_sub;                       // level -> first sub-level (size nlevels + 1)
     Fr* d_coeff_invs = nullptr;

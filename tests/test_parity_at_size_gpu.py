@@ -203,6 +203,24 @@ def test_device_solver_kernels_agree(ctx, audit, monkeypatch):
     circ_w.free()
 
 
+def test_rows_longer_than_the_product_buffer(ctx, monkeypatch):
+    """Rows with more non-unit terms (1,100) than k_solve_2p's shared product buffer holds (1,024) multiply in place:
+    the device solver's wires equal the host solver's, with and without the thread-per-proof kernel."""
+    from shielded_pool_pinocchio_solana_b200 import synth
+    sc = synth.build(60, n_public=2, n_secret=16, n_committed=8, seed=3, dens_b=1100)
+    pk, _ = ctx.setup(sc.ccs, b"long-rows")
+    circ = ctx.load_circuit(sc.ccs, pk)
+    assert circ.solver == "gpu", circ.solver
+    n = 5
+    asg = b"".join(sc.assignment_bytes(40 + i) for i in range(n))
+    rnd = b"".join(rnd_for(950 + i) for i in range(n))
+    want = circ.witness_batch(asg, n, rnd)
+    assert circ.witness_batch_dev(asg, n, rnd) == want
+    monkeypatch.setenv("G16_SOLVER_NARROW", "0")
+    assert circ.witness_batch_dev(asg, n, rnd) == want
+    circ.free()
+
+
 def test_withdraw_circuit_solves_on_the_device(ctx, monkeypatch):
     """The reference's withdraw circuit takes the DEVICE solver: its three integer hints (Grumpkin scalar split, limb
     decomposition, emulated product) hang off an input wire, are evaluated on the host per proof and scattered into the
