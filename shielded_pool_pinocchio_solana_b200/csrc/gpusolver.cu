@@ -4,12 +4,15 @@
 // gnark walks the instruction levels with goroutines; on a 16-core host that costs 10-20 ms per
 // audit-size proof and caps a box at a few hundred proofs/s -- less than ONE B200 proves.  Here the
 // level structure is compiled once per circuit into a static plan (which wire each row defines is
-// independent of the witness), and a CTA per proof executes it: four lanes share a row of a level
-// (median ~20 rows per level in the reference circuit), __syncthreads() separates levels, wires live in
-// HBM in the layout the prover reads.  The solve is latency-bound (~10^3 dependent levels of ~10 dependent
-// modmuls when one thread owns a row), so the plan is flattened into per-level records (one 32-byte record
-// per instruction) to keep the chain of dependent loads at record -> terms -> wires, and the terms of a row
-// are spread over lanes so that their loads and products run side by side (k_solve_tpi).
+// independent of the witness) and executed for a whole group of proofs, wires in HBM in the layout the
+// prover reads.  Three kernels share the plan (GpuSolverPlan::run picks per level range):
+//   k_solve_2p      wide levels: CTA per proof; the non-unit products of a (sub-)level by one thread each into
+//                   shared memory, then one thread per row sums its operands and finishes the row (default)
+//   k_solve_narrow  runs of thin levels (the division chain at the end of the withdraw circuit): thread per proof
+//   k_solve_tpi     the previous wide kernel: four lanes per row (G16_SOLVER_TPI=1); k_solve_levels: round 1's
+//                   thread per row (G16_SOLVER_CTA=1).  Both kept as cross-checks (tests/test_parity_at_size_gpu.py).
+// Alone the solve is latency-bound (~10^3 dependent levels); beside the prover it also competes for issue slots,
+// which is why the default kernels issue as few instructions as they can (pipeline section).
 // The BSB22 commitment splits the plan in two phases (prove.cu runs the commitment MSM between).
 // Circuits using a hint this file does not implement keep the host solver (solver.cpp).
 #include "gpusolver.cuh"
