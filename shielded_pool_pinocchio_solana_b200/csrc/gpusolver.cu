@@ -728,7 +728,9 @@ int GpuSolverPlan::build(const Circuit& c, cudaStream_t st, std::string* why_not
         for (uint32_t lv = 0; lv < nlevels;) {
             uint32_t e = lv;
             while (e < nlevels && thin[e] == thin[lv]) e++;
-            const bool narrow = thin[lv] && e - lv >= min_run;
+            // a thread walks the rows of a run one after the other (~3 us each) where the wide kernel pays ~5 us per
+            // level: worth its small footprint only while the levels average a few rows
+            const bool narrow = thin[lv] && e - lv >= min_run && lvl_off[e] - lvl_off[lv] <= 3 * (e - lv);
             if (!segments.empty() && segments.back().narrow == narrow) segments.back().end = e;
             else segments.push_back({lv, e, narrow});
             lv = e;

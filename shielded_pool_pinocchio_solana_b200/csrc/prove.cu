@@ -225,14 +225,17 @@ __device__ G1XYZZ g1_scalar_mul(const G1Affine& p, const Fr& k) {
     return acc;
 }
 
-// The two 254-bit scalar multiplications of the Krs assembly, s*Ar and r*Bs1: ~3.5 K dependent modmuls each
-// (1.2 ms).  One 64-thread CTA per proof, one scalar per warp (no divergence between the two ladders).  Runs on
-// the side stream right behind the A and B1 MSMs, i.e. under the quotient and the K|Z MSM of the main stream.
-__global__ void __launch_bounds__(64)
+// The two 254-bit scalar multiplications of the Krs assembly, s*Ar and r*Bs1: ~3.5 K dependent modmuls each.
+// One THREAD per ladder (2B threads): the step is issue-bound, and a warp with one working lane costs as many issue
+// slots as a full one -- a CTA per proof with one ladder per warp was 1.5 % of a step's instructions for 128 ladders.
+// Lanes diverge on the scalar bits (a warp runs the addition at every bit), which lengthens a ladder by a third; it
+// runs on the side stream right behind the A and B1 MSMs, under the quotient and the K|Z MSM of the main stream.
+__global__ void __launch_bounds__(32)
 k_scalar_muls(const G1Affine* __restrict__ ar, const G1Affine* __restrict__ bs1, const Fr* __restrict__ wires,
-              size_t wstride, size_t nw, uint32_t stride_b, G1XYZZ* __restrict__ parts) {
-    const uint32_t b = blockIdx.x, which = threadIdx.x >> 5;
-    if (threadIdx.x & 31) return;
+              size_t wstride, size_t nw, uint32_t stride_b, uint32_t B, G1XYZZ* __restrict__ parts) {
+    const uint32_t idx = blockIdx.x * 32 + threadIdx.x;
+    if (idx >= 2 * B) return;
+    const uint32_t b = idx >> 1, which = idx & 1;
     const Fr* x = wires + (size_t)b * wstride + nw;
     const Fr k = (which == 0 ? x[X_S] : x[X_R]).from_mont();
     parts[(size_t)which * stride_b + b] = g1_scalar_mul(which == 0 ? ar[b] : bs1[b], k);
@@ -453,7 +456,7 @@ int prove_device(g16_circuit* c, size_t B, const Fr* W, int p) {
             G16_CUDA(cudaStreamWaitEvent(sSm, c->ev_join[g16_circuit::SIDE_A], 0));
             G16_CUDA(cudaStreamWaitEvent(sSm, c->ev_join[g16_circuit::SIDE_B1], 0));
         }
-        k_scalar_muls<<<(unsigned)B, 64, 0, sSm>>>(rA, rB1, W, c->wstride, c->nw, (uint32_t)c->max_batch, parts);
+        k_scalar_muls<<<cdiv(2 * B, 32), 32, 0, sSm>>>(rA, rB1, W, c->wstride, c->nw, (uint32_t)c->max_batch, (uint32_t)B, parts);
         ctx->prof.mark("scalar_muls", "done", sSm);
         launches++;
     }
@@ -488,7 +491,7 @@ int prove_device(g16_circuit* c, size_t B, const Fr* W, int p) {
     if (ctx->world > 1) {   // partial sums of this rank's point ranges -> sums over all ranks (tiny NCCL all-gather)
         G16_TRY(comm_sum_points<Fp>(ctx, c->d_tmp_g1[p], 4 * c->max_batch, sFin));
         G16_TRY(comm_sum_points<Fp2>(ctx, rB2, c->max_batch, sFin));
-        k_scalar_muls<<<(unsigned)B, 64, 0, sFin>>>(rA, rB1, W, c->wstride, c->nw, (uint32_t)c->max_batch, parts);
+        k_scalar_muls<<<cdiv(2 * B, 32), 32, 0, sFin>>>(rA, rB1, W, c->wstride, c->nw, (uint32_t)c->max_batch, (uint32_t)B, parts);
         launches += 3;
     }
     k_finalize<<<(unsigned)B, 32, 0, sFin>>>(rA, parts, (uint32_t)c->max_batch, rB2, rKZ, rPok, (ProofPoints*)c->d_out[p].ptr);
