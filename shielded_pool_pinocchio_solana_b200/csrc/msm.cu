@@ -145,7 +145,10 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     const size_t hot_cap = nentries / cap + 1;
     // ---- bucket reduction shape ----------------------------------------------------------------
     uint32_t seg = 64;
-    while (seg > 4 && nbuckets / seg < 65536) seg >>= 1;
+#ifndef MSM_MIN_SEG
+#define MSM_MIN_SEG 4
+#endif
+    while (seg > MSM_MIN_SEG && nbuckets / seg < 65536) seg >>= 1;
     if (seg > cfg.nb) seg = cfg.nb;
     const uint32_t nseg = cfg.nb / seg;
     const size_t nseg_total = batch * nseg;
@@ -255,7 +258,10 @@ int MsmRunner<F>::run(const MsmBases<F>& bases, const Fr* d_scalars, size_t stri
     // ---- bucket reduction ------------------------------------------------------------------------------------
     k_msm_reduce1<F><<<cdiv(nseg_total, 128), 128, 0, st>>>(result_vb, vbase, seg, (uint32_t)nseg_total, seg_acc, seg_run);
     k_msm_reduce2<F><<<(unsigned)(batch * parts), MSM_R2_THREADS, 0, st>>>(seg_acc, seg_run, nseg, parts, per, part_out);
-    k_msm_reduce3<F><<<(unsigned)batch, 32, 0, st>>>(part_out, parts, seg, d_out);
+    if (parts == 1 && batch >= 32)
+        k_msm_reduce3_flat<F><<<cdiv(batch, 32), 32, 0, st>>>(part_out, (uint32_t)batch, seg, d_out);
+    else
+        k_msm_reduce3<F><<<(unsigned)batch, 32, 0, st>>>(part_out, parts, seg, d_out);
     launches += 3;
     if (prof) prof->mark(label, "reduced", st);
     G16_CUDA(cudaGetLastError());
